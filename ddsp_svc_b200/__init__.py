@@ -1,0 +1,8 @@
+"""ddsp_svc_b200 -- B200 (sm_100a) kernels for the DDSP harmonic-plus-noise synthesis path of
+yxlllc/DDSP-SVC, behind the reference's Sins / CombSub / CombSubSuperFast / SineGen forward()
+API.  See DESIGN.md for the path, its boundary and the kernels; include/b200ddsp.h for the C ABI.
+"""
+from . import _lib, ops, synthetic  # noqa: F401
+from .vocoder import FixedControls, Sins  # noqa: F401
+
+__all__ = ["Sins", "FixedControls", "ops", "synthetic"]

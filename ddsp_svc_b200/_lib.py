@@ -1,0 +1,113 @@
+"""ctypes binding of libb200ddsp.so (the C ABI declared in include/b200ddsp.h).
+
+The library is built in-tree by ``build()`` (nvcc, sm_100a only) and travels with the repo.
+There is NO fallback: if the shared library is missing or fails to load, importing the ops
+raises -- the product path never degrades to PyTorch or to the oracle.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libb200ddsp.so")
+HEADER = os.path.join(ROOT, "include", "b200ddsp.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+c_f32p = ctypes.c_void_p   # device pointers travel as integers
+c_f64p = ctypes.c_void_p
+c_stream = ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/b200ddsp.h declares
+SIGNATURES = {
+    "b2d_version": (ctypes.c_int, []),
+    "b2d_last_error": (ctypes.c_char_p, []),
+    "b2d_phase_scan": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_int, c_f64p, c_f32p, c_stream]),
+    "b2d_sins_bank": (ctypes.c_int, [c_f32p, c_f64p, c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_f32p, c_stream]),
+    "b2d_dft_tables_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "b2d_dft_tables": (ctypes.c_int, [ctypes.c_int, c_f32p, c_stream]),
+    "b2d_ir_build": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, c_f32p, c_f32p, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_double, c_f32p, c_stream]),
+    "b2d_ltv_fir": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_int, c_f32p,
+                                   c_f32p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, c_stream]),
+    "b2d_ltv_fir_generic": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, c_f32p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, c_stream]),
+    "b2d_sins_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "b2d_sins_synth": (ctypes.c_int, [c_f32p, c_f64p, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p,
+                                      ctypes.c_uint64, ctypes.c_int64, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_size_t,
+                                      c_stream]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into ddsp_svc_b200/libb200ddsp.so (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError(
+                    "libb200ddsp.so is missing (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                    "there is no CPU or PyTorch fallback for the synthesis kernels." % LIB_PATH)
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)   # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+class B2DError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    """0 ok; <0 argument error -> ValueError (the reference raises ValueError for shape
+    mismatches, ddsp/core.py:151-153); >0 CUDA error -> RuntimeError."""
+    if rc == 0:
+        return
+    msg = lib().b2d_last_error()
+    msg = msg.decode("utf-8", "replace") if msg else ""
+    if rc < 0:
+        raise ValueError("%s failed (%d): %s" % (what, rc, msg))
+    raise B2DError("%s failed (cudaError %d): %s" % (what, rc, msg))

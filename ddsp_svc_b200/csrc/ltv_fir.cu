@@ -1,0 +1,337 @@
+// K4: linear time-varying FIR  (reference ddsp/core.py:120-182, fft_convolve).
+//
+//   y[n] = sum_tau ((1-phi_m) h_f[tau] + phi_m h_{f+1}[tau]) x[m],   m = n + L/2 - tau,
+//   f = floor(m/P), phi_m = (m mod P)/P, h_{nF} := h_{nF-1}, x = 0 outside [0,T)
+//
+// (the reference's Bartlett-windowed 50%-overlap FFT overlap-add is exactly this linear
+// interpolation of the per-frame impulse responses along the INPUT index m; only the
+// linear-convolution result is reproduced, not its 1533-point FFT).
+//
+// Tiling.  A CTA computes P consecutive outputs n = f P - (L/2+1) + i, i in [0,P).  The tap
+// range is cut into segments of P taps; for segment s the inputs are m = g P - 1 + i - tau'
+// with g = f - s, tau' in [0,P): they span exactly the two frames g-1 and g, the switch being
+// at tau' = i.  Writing the interpolation weight as (i-1-tau')/P = (i-1)/P - tau'/P,
+//
+//   y[i] += sum_tau' x[m] G[tau'] + ((i-1)/P) sum_tau' x[m] E[tau'],
+//   (G,E) = (h_g - (tau'/P) D_g,     D_g = h_{g+1} - h_g)     for tau' <  i   ("A" tables)
+//         = (h_g - (tau'/P) D_{g-1}, D_{g-1} = h_g - h_{g-1}) for tau' >= i   ("B" tables)
+//
+// so each (output, tap) pair costs exactly 2 FMAs on ONE input sample and two small per-tile
+// tables that are built once in shared memory.  A thread owns 8 consecutive outputs and slides
+// a 12-sample register window over the input (one 128-bit shared load per 4 taps, XOR-swizzled
+// so the stride-8 lane pattern is conflict-free); the table entries are warp-broadcast 128-bit
+// loads.  Lanes switch from the A to the B tables at different taps, so the loop body is kept
+// uniform (pointer select per step) and the <8-tap band where a thread's outputs straddle the
+// switch is fixed up afterwards.  Per 4 taps and thread: 64 FFMA, 3 LDS.128, ~8 integer ops.
+//
+// Two filters ("jobs") with the same tap count can run in one CTA (Sins: harmonic all-pass and
+// noise filter); their outputs are summed through shared memory into `mix` (+ an optional
+// addend), so signal = harmonic + noise (ddsp/vocoder.py:609) needs no extra pass.
+// White noise input is generated in-kernel (Philox4x32-10) when the job has no input pointer.
+#include <algorithm>
+
+#include "b2d_common.cuh"
+
+namespace {
+
+struct FirJob {
+    const float* x;   // [B,T] or nullptr -> in-kernel uniform noise
+    const float* ir;  // [B,nF,L]
+    float* y;         // [B,T] or nullptr
+    int L;
+};
+
+struct FirParams {
+    FirJob job[2];
+    int njobs;
+    const float* addend;  // [B,T] or nullptr
+    float* mix;           // [B,T] or nullptr
+    unsigned long long seed;
+    long long utt_off;
+    int nF, P, T;
+};
+
+__device__ __forceinline__ int swz(int q) {  // logical float index -> physical (16B-chunk XOR swizzle)
+    const int c = q >> 2;
+    return ((c ^ ((c >> 3) & 1)) << 2) | (q & 3);
+}
+__device__ __forceinline__ float4 lds4(const float* xs, int chunk) {
+    return *reinterpret_cast<const float4*>(xs + ((chunk ^ ((chunk >> 3) & 1)) << 2));
+}
+
+__device__ __forceinline__ void fir_step(const float4& lo, const float4& mid, const float4& hi, const float4& t0,
+                                         const float4& t1, float (&a1)[8], float (&a2)[8]) {
+    const float W[12] = {lo.x, lo.y, lo.z, lo.w, mid.x, mid.y, mid.z, mid.w, hi.x, hi.y, hi.z, hi.w};
+    const float G[4] = {t0.x, t0.z, t1.x, t1.z};
+    const float E[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float xv = W[3 + r - tt];
+            a1[r] = fmaf(xv, G[tt], a1[r]);
+            a2[r] = fmaf(xv, E[tt], a2[r]);
+        }
+    }
+}
+
+__device__ __forceinline__ void job_barrier(int job, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(job + 1), "r"(nthreads) : "memory");
+}
+
+// threads per job = P/8.  smem per job: xs[2P] + tabA[2P] + pad[8] + tabB[2P]; then ybuf[2][P].
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int P = p.P, T = p.T, nF = p.nF;
+    const int TPJ = P >> 3;
+    const int job = threadIdx.x / TPJ;
+    const int lt = threadIdx.x - job * TPJ;
+    const int b = blockIdx.y, f = blockIdx.x;
+    const int per_job = 6 * P + 8;
+    float* xs = sm + job * per_job;
+    float* tabA = xs + 2 * P;
+    float* tabB = tabA + 2 * P + 8;
+    float* ybuf = sm + p.njobs * per_job;  // [njobs][P]
+
+    FirJob jb;  // select by value: dynamic indexing of kernel params would spill them to local memory
+    jb.x = job ? p.job[1].x : p.job[0].x;
+    jb.ir = job ? p.job[1].ir : p.job[0].ir;
+    jb.y = job ? p.job[1].y : p.job[0].y;
+    jb.L = job ? p.job[1].L : p.job[0].L;
+    const int L = jb.L, Mh = L / 2 + 1;
+    const int NS = (L + P - 1) / P;
+    const int i0 = lt << 3;
+    const float invP = 1.0f / (float)P;
+    const float* xrow = jb.x ? jb.x + (size_t)b * T : nullptr;
+    const float* irb = jb.ir + (size_t)b * nF * L;
+
+    float a1[8], a2[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a1[r] = a2[r] = 0.f;
+
+    for (int s = 0; s < NS; ++s) {
+        const int g = f - s;
+        if (g < 0 || g > nF) continue;  // all inputs of this segment are outside [0,T)
+        job_barrier(job, TPJ);          // previous segment's readers are done
+        // ---- input tile m in [gP-P, gP+P) -> xs (swizzled) ----
+        const int mbase = g * P - P;
+        for (int c = lt; c < (P >> 1); c += TPJ) {
+            const int m = mbase + (c << 2);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m >= 0 && m < T) {  // T and m are multiples of 4: whole quad in range
+                if (xrow) v = __ldg(reinterpret_cast<const float4*>(xrow + m));
+                else v = b2d::philox_uniform_pm1(p.seed, (unsigned long long)(p.utt_off + b), (uint32_t)(m >> 2));
+            }
+            *reinterpret_cast<float4*>(xs + ((c ^ ((c >> 3) & 1)) << 2)) = v;
+        }
+        // ---- tables for taps tau = sP + tau' ----
+        const float* hm = irb + (size_t)min(max(g - 1, 0), nF - 1) * L;
+        const float* h0 = irb + (size_t)min(max(g, 0), nF - 1) * L;
+        const float* hp = irb + (size_t)min(max(g + 1, 0), nF - 1) * L;
+        for (int tp = lt; tp < P; tp += TPJ) {
+            const int tau = s * P + tp;
+            float vm = 0.f, v0 = 0.f, vp = 0.f;
+            if (tau < L) { vm = __ldg(hm + tau); v0 = __ldg(h0 + tau); vp = __ldg(hp + tau); }
+            const float w = (float)tp * invP;
+            const float eA = vp - v0, eB = v0 - vm;
+            tabA[2 * tp] = fmaf(-w, eA, v0);
+            tabA[2 * tp + 1] = eA;
+            tabB[2 * tp] = fmaf(-w, eB, v0);
+            tabB[2 * tp + 1] = eB;
+        }
+        job_barrier(job, TPJ);
+
+        // ---- main loop: P/4 steps of 4 taps ----
+        const float4* tA = reinterpret_cast<const float4*>(tabA);
+        const float4* tB = reinterpret_cast<const float4*>(tabB);
+        const int c0 = (P >> 2) - 1 + (lt << 1);  // chunk of logical q = P-4+i0
+        const int sw = lt << 1;                   // steps < sw use the A tables (tau0 < i0)
+        const int nsteps = P >> 2;
+        float4 A = lds4(xs, c0 + 1), Bv = lds4(xs, c0 + 2), C;
+        int step = 0;
+        for (; step + 3 <= nsteps; step += 3) {
+            {
+                const float4* tp4 = (step < sw) ? tA : tB;
+                const float4 t0 = tp4[2 * step], t1 = tp4[2 * step + 1];
+                C = lds4(xs, c0 - step);
+                fir_step(C, A, Bv, t0, t1, a1, a2);
+            }
+            {
+                const float4* tp4 = (step + 1 < sw) ? tA : tB;
+                const float4 t0 = tp4[2 * step + 2], t1 = tp4[2 * step + 3];
+                Bv = lds4(xs, c0 - step - 1);
+                fir_step(Bv, C, A, t0, t1, a1, a2);
+            }
+            {
+                const float4* tp4 = (step + 2 < sw) ? tA : tB;
+                const float4 t0 = tp4[2 * step + 4], t1 = tp4[2 * step + 5];
+                A = lds4(xs, c0 - step - 2);
+                fir_step(A, Bv, C, t0, t1, a1, a2);
+            }
+        }
+        if (step < nsteps) {
+            const float4* tp4 = (step < sw) ? tA : tB;
+            const float4 t0 = tp4[2 * step], t1 = tp4[2 * step + 1];
+            C = lds4(xs, c0 - step);
+            fir_step(C, A, Bv, t0, t1, a1, a2);
+            ++step;
+            if (step < nsteps) {
+                const float4* tq4 = (step < sw) ? tA : tB;
+                const float4 u0 = tq4[2 * step], u1 = tq4[2 * step + 1];
+                Bv = lds4(xs, c0 - step);
+                fir_step(Bv, C, A, u0, u1, a1, a2);
+            }
+        }
+        // ---- band fix-up: taps tau' in [i0, i0+r) belong to the A tables for output r ----
+#pragma unroll
+        for (int bb = 0; bb < 7; ++bb) {
+            const int tp = i0 + bb;
+            const float dG = tabA[2 * tp] - tabB[2 * tp];
+            const float dE = tabA[2 * tp + 1] - tabB[2 * tp + 1];
+#pragma unroll
+            for (int r = bb + 1; r < 8; ++r) {
+                const float xv = xs[swz(P - 1 + r - bb)];
+                a1[r] = fmaf(xv, dG, a1[r]);
+                a2[r] = fmaf(xv, dE, a2[r]);
+            }
+        }
+    }
+
+    // ---- combine, store, mix ----
+    float yv[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) yv[r] = fmaf((float)(i0 + r - 1) * invP, a2[r], a1[r]);
+
+    const int n0 = f * P - Mh + i0;
+    const bool vec_ok = ((n0 & 3) == 0) && n0 >= 0 && (n0 + 8) <= T;
+    if (jb.y) {
+        float* yrow = jb.y + (size_t)b * T;
+        if (vec_ok) {
+            b2d::st_global_v4(yrow + n0, make_float4(yv[0], yv[1], yv[2], yv[3]));
+            b2d::st_global_v4(yrow + n0 + 4, make_float4(yv[4], yv[5], yv[6], yv[7]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (n0 + r >= 0 && n0 + r < T) yrow[n0 + r] = yv[r];
+        }
+    }
+    if (p.mix) {
+        if (p.njobs > 1) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ybuf[job * P + i0 + r] = yv[r];
+            __syncthreads();
+        }
+        if (job == 0) {
+            float* mrow = p.mix + (size_t)b * T;
+            const float* arow = p.addend ? p.addend + (size_t)b * T : nullptr;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float v = yv[r];
+                if (p.njobs > 1) v += ybuf[P + i0 + r];
+                if (arow && n0 + r >= 0 && n0 + r < T) v += arow[n0 + r];
+                yv[r] = v;
+            }
+            if (vec_ok) {
+                b2d::st_global_v4(mrow + n0, make_float4(yv[0], yv[1], yv[2], yv[3]));
+                b2d::st_global_v4(mrow + n0 + 4, make_float4(yv[4], yv[5], yv[6], yv[7]));
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (n0 + r >= 0 && n0 + r < T) mrow[n0 + r] = yv[r];
+            }
+        }
+    }
+}
+
+// One thread per output sample, straight from the definition.  Any P / L.
+__global__ void ltv_fir_generic_kernel(const float* __restrict__ x, const float* __restrict__ ir, int L,
+                                       float* __restrict__ y, int nF, int P, int T) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= T) return;
+    const float* xr = x + (size_t)b * T;
+    const float* irb = ir + (size_t)b * nF * L;
+    const float invP = 1.0f / (float)P;
+    float acc = 0.f;
+    for (int tau = 0; tau < L; ++tau) {
+        const int m = n + L / 2 - tau;
+        if (m < 0 || m >= T) continue;
+        const int fr = m / P;
+        const float phi = (float)(m - fr * P) * invP;
+        const float ha = irb[(size_t)fr * L + tau];
+        const float hb = irb[(size_t)min(fr + 1, nF - 1) * L + tau];
+        acc = fmaf(xr[m], fmaf(phi, hb - ha, ha), acc);
+    }
+    y[(size_t)b * T + n] = acc;
+}
+
+}  // namespace
+
+namespace b2d {
+
+// internal entry (also used by the CombSub driver): mix = y1 (+ y2) (+ addend)
+int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
+                   int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
+                   int nF, int P, cudaStream_t st) {
+    if (!ir1) return fail(B2D_ERR_NULL, "ltv_fir: ir1 is null");
+    if (B <= 0 || nF <= 0 || P <= 0 || taps1 <= 0 || (taps1 & 1)) return fail(B2D_ERR_SHAPE, "ltv_fir: bad shape");
+    if (P % 256 != 0 || P > 2048)
+        return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: tiled kernel needs block size multiple of 256 (got %d); use b2d_ltv_fir_generic", P);
+    if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: batch %d > 65535", B);
+    const int njobs = ir2 ? 2 : 1;
+    if (njobs == 2) {
+        if (taps2 <= 0 || (taps2 & 1)) return fail(B2D_ERR_SHAPE, "ltv_fir: bad taps2");
+        // each job's output tile starts at fP - (L/2+1): only equal tap counts share a tile
+        if (taps1 != taps2)
+            return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: two jobs must have the same tap count (got %d, %d)", taps1, taps2);
+        if (njobs * (P / 8) > 512) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: block size too large for two jobs");
+    }
+    const float* ptrs[] = {x1, x2, y1, y2, addend, mix};
+    for (const float* q : ptrs)
+        if (q && !aligned16(q)) return fail(B2D_ERR_ALIGN, "ltv_fir: signal pointers must be 16-byte aligned");
+    FirParams p;
+    p.job[0] = {x1, ir1, y1, taps1};
+    p.job[1] = {x2, ir2, y2, njobs == 2 ? taps2 : taps1};
+    p.njobs = njobs;
+    p.addend = addend;
+    p.mix = mix;
+    p.seed = seed;
+    p.utt_off = utt_off;
+    p.nF = nF; p.P = P; p.T = nF * P;
+    const int Mh = taps1 / 2 + 1;
+    const int ntiles = nF + (Mh + P - 1) / P;
+    const size_t smem = (size_t)(njobs * (6 * P + 8) + njobs * P) * sizeof(float);
+    const int threads = njobs * (P / 8);
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "ltv_fir: smem attr: %s", cudaGetErrorString(e));
+        }
+        kern<<<dim3(ntiles, B), threads, smem, st>>>(p);
+        return check_launch("ltv_fir");
+    };
+    // register budget: 80/thread is spill-free; more resident CTAs hide the table-build prologue
+    if (threads <= 128) return go(ltv_fir_kernel<128, 6>);
+    if (threads <= 256) return go(ltv_fir_kernel<256, 3>);
+    return go(ltv_fir_kernel<512, 1>);
+}
+
+}  // namespace b2d
+
+extern "C" int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1, const float* x2,
+                           const float* ir2, int taps2, float* y2, float* mix, uint64_t seed,
+                           int64_t utterance_offset, int B, int n_frames, int block, void* stream) {
+    return b2d::ltv_fir_launch(x1, ir1, taps1, y1, x2, ir2, taps2, y2, nullptr, mix, seed, utterance_offset, B,
+                               n_frames, block, (cudaStream_t)stream);
+}
+
+extern "C" int b2d_ltv_fir_generic(const float* x, const float* ir, int taps, float* y, int B, int n_frames,
+                                   int block, void* stream) {
+    if (!x || !ir || !y) return b2d::fail(B2D_ERR_NULL, "ltv_fir_generic: null pointer");
+    if (B <= 0 || n_frames <= 0 || block <= 0 || taps <= 0) return b2d::fail(B2D_ERR_SHAPE, "ltv_fir_generic: bad shape");
+    if (B > 65535) return b2d::fail(B2D_ERR_UNSUPPORTED, "ltv_fir_generic: batch %d > 65535", B);
+    const int T = n_frames * block;
+    ltv_fir_generic_kernel<<<dim3((T + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(x, ir, taps, y, n_frames, block, T);
+    return b2d::check_launch("ltv_fir_generic");
+}

@@ -1,0 +1,186 @@
+"""Thin tensor-level wrappers over the C ABI: PyTorch CUDA tensors in, PyTorch CUDA tensors out.
+
+PyTorch is only the plumbing here (device memory from its caching allocator, the current
+stream); all arithmetic happens in libb200ddsp.so.  Every function requires CUDA fp32 inputs
+and raises otherwise -- there is no CPU path.
+"""
+import threading
+
+import torch
+
+from . import _lib
+
+IR_ALLPASS, IR_MAG_HANN, IR_MAG_DYNAMIC = 0, 1, 2
+
+# kernel launches issued through this module (bench.py reports it as gpu_launches)
+_launches = 0
+_tables = {}
+_tables_lock = threading.Lock()
+
+
+def launches():
+    return _launches
+
+
+def _count(n):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda_f32(name, t, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (the B200 kernels have no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def _frames_2d(f0_frames):
+    """[B, nF, 1] or [B, nF] -> contiguous [B, nF]."""
+    _need_cuda_f32("f0_frames", f0_frames)
+    f0 = f0_frames.squeeze(-1) if f0_frames.dim() == 3 else f0_frames
+    if f0.dim() != 2:
+        raise ValueError("f0_frames must be [B, n_frames, 1] or [B, n_frames]")
+    return f0.contiguous()
+
+
+def _ctrl_view(name, c, B, nF):
+    """A raw control tensor [B, nF, C] that is a strided view of the dense Unit2Control output
+    (torch.split, reference ddsp/unit2control.py:22): returns (tensor, frame stride)."""
+    _need_cuda_f32(name, c)
+    if c.dim() != 3 or c.shape[0] != B or c.shape[1] != nF:
+        raise ValueError("Batch/frame size of %s %s does not match f0 (%d, %d)" % (name, tuple(c.shape), B, nF))
+    if c.stride(2) != 1 or (B > 1 and c.stride(0) != nF * c.stride(1)) or c.stride(1) < c.shape[2]:
+        c = c.contiguous()
+    return c, c.stride(1)
+
+
+def dft_tables(n_mag, device):
+    """Constant cos/sin matrices of the 2(n_mag-1)-point inverse real DFT, cached per device."""
+    key = (int(n_mag), torch.device(device).index)
+    with _tables_lock:
+        t = _tables.get(key)
+        if t is None:
+            L = _lib.lib()
+            nbytes = L.b2d_dft_tables_bytes(int(n_mag))
+            if nbytes == 0:
+                raise ValueError("n_mag=%d out of range" % n_mag)
+            t = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+            _lib.check(L.b2d_dft_tables(int(n_mag), t.data_ptr(), _stream()), "b2d_dft_tables")
+            _count(1)
+            _tables[key] = t
+    return t
+
+
+def phase_scan(f0_frames, block, sampling_rate, initial_phase=None, infer=True):
+    """-> (frame_phase fp64 [B, nF] unwrapped cycles, phase_frames fp32 [B, nF, 1] radians)."""
+    f0 = _frames_2d(f0_frames)
+    B, nF = f0.shape
+    ip = None
+    if initial_phase is not None:
+        ip = initial_phase.to(device=f0.device, dtype=torch.float32).reshape(-1).contiguous()
+        if ip.numel() == 1 and B > 1:
+            ip = ip.expand(B).contiguous()
+        if ip.numel() != B:
+            raise ValueError("initial_phase must have one value per utterance")
+    frame_phase = torch.empty(B, nF, dtype=torch.float64, device=f0.device)
+    phase_frames = torch.empty(B, nF, 1, dtype=torch.float32, device=f0.device)
+    rc = _lib.lib().b2d_phase_scan(f0.data_ptr(), _ptr(ip), B, nF, int(block), float(sampling_rate),
+                                   0 if infer else 1, frame_phase.data_ptr(), phase_frames.data_ptr(), _stream())
+    _lib.check(rc, "b2d_phase_scan")
+    _count(1)
+    return frame_phase, phase_frames
+
+
+def sins_bank(f0_frames, frame_phase, c_amp, block, sampling_rate, infer=True):
+    f0 = _frames_2d(f0_frames)
+    B, nF = f0.shape
+    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    c, stride = _ctrl_view("amplitudes", c_amp, B, nF)
+    out = torch.empty(B, nF * block, dtype=torch.float32, device=f0.device)
+    rc = _lib.lib().b2d_sins_bank(f0.data_ptr(), frame_phase.data_ptr(), c.data_ptr(), stride, B, nF, int(block),
+                                  c.shape[2], float(sampling_rate), 0 if infer else 1, out.data_ptr(), _stream())
+    _lib.check(rc, "b2d_sins_bank")
+    _count(1)
+    return out
+
+
+def ir_build(c_raw, mode, sampling_rate, f0_frames=None):
+    """raw control [B, nF, M] -> impulse responses [B, nF, 2(M-1)]."""
+    _need_cuda_f32("control", c_raw)
+    B, nF, M = c_raw.shape
+    c, stride = _ctrl_view("control", c_raw, B, nF)
+    f0 = _frames_2d(f0_frames) if f0_frames is not None else None
+    ir = torch.empty(B, nF, 2 * (M - 1), dtype=torch.float32, device=c.device)
+    tab = dft_tables(M, c.device)
+    rc = _lib.lib().b2d_ir_build(c.data_ptr(), stride, int(mode), _ptr(f0), tab.data_ptr(), B, nF, M,
+                                 float(sampling_rate), ir.data_ptr(), _stream())
+    _lib.check(rc, "b2d_ir_build")
+    _count(1)
+    return ir
+
+
+def ltv_fir(x, ir, block, seed=0, utterance_offset=0, generic=False):
+    """Time-varying FIR of x [B, T] (or None = in-kernel uniform noise) with ir [B, nF, L]."""
+    _need_cuda_f32("ir", ir)
+    ir = ir.contiguous()
+    B, nF, L = ir.shape
+    if x is not None:
+        _need_cuda_f32("x", x)
+        if x.shape[0] != B:
+            raise ValueError("Batch size of audio ({}) and impulse response ({}) must be the same."
+                             .format(x.shape[0], B))
+        x = x.contiguous()
+    y = torch.empty(B, nF * block, dtype=torch.float32, device=ir.device)
+    Lh = _lib.lib()
+    if generic:
+        rc = Lh.b2d_ltv_fir_generic(_ptr(x), ir.data_ptr(), L, y.data_ptr(), B, nF, int(block), _stream())
+    else:
+        rc = Lh.b2d_ltv_fir(_ptr(x), ir.data_ptr(), L, y.data_ptr(), 0, 0, 0, 0, 0, int(seed),
+                            int(utterance_offset), B, nF, int(block), _stream())
+    _lib.check(rc, "b2d_ltv_fir")
+    _count(1)
+    return y
+
+
+def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sampling_rate, noise_in=None,
+               seed=0, utterance_offset=0, infer=True, want_parts=True):
+    """Whole Sins DSP after Unit2Control -> (signal, harmonic, noise) [B, T] each."""
+    f0 = _frames_2d(f0_frames)
+    B, nF = f0.shape
+    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    ca, s0 = _ctrl_view("amplitudes", c_amp, B, nF)
+    cg, s1 = _ctrl_view("group_delay", c_group_delay, B, nF)
+    cn, s2 = _ctrl_view("noise_magnitude", c_noise, B, nF)
+    if not (s0 == s1 == s2):  # views of different tensors: densify so one stride describes all
+        ca, cg, cn = ca.contiguous(), cg.contiguous(), cn.contiguous()
+        dense = torch.cat((ca, cg, cn), dim=-1)
+        ca, cg, cn = torch.split(dense, [ca.shape[2], cg.shape[2], cn.shape[2]], dim=-1)
+        s0 = dense.stride(1)
+    H, Ma, Mn = ca.shape[2], cg.shape[2], cn.shape[2]
+    dev = f0.device
+    T = nF * block
+    if noise_in is not None:
+        _need_cuda_f32("noise_in", noise_in)
+        noise_in = noise_in.reshape(B, T).contiguous()
+    L = _lib.lib()
+    ws_bytes = L.b2d_sins_workspace_bytes(B, nF, int(block), Ma, Mn)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    signal = torch.empty(B, T, dtype=torch.float32, device=dev)
+    harmonic = torch.empty(B, T, dtype=torch.float32, device=dev) if want_parts else None
+    noise = torch.empty(B, T, dtype=torch.float32, device=dev) if (want_parts or Ma != Mn) else None
+    ta, tn = dft_tables(Ma, dev), dft_tables(Mn, dev)
+    rc = L.b2d_sins_synth(f0.data_ptr(), frame_phase.data_ptr(), ca.data_ptr(), cg.data_ptr(), cn.data_ptr(), s0,
+                          _ptr(noise_in), int(seed), int(utterance_offset), ta.data_ptr(), tn.data_ptr(), B, nF,
+                          int(block), H, Ma, Mn, float(sampling_rate), 0 if infer else 1, signal.data_ptr(),
+                          _ptr(harmonic), _ptr(noise), ws.data_ptr(), ws_bytes, _stream())
+    _lib.check(rc, "b2d_sins_synth")
+    _count(4 if Ma == Mn else 5)
+    return signal, harmonic, noise

@@ -1,0 +1,101 @@
+"""Drop-in synthesizer modules: same constructor arguments, buffers (state-dict keys) and
+forward() contract as the reference's ddsp/vocoder.py classes, with the DSP executed by the
+sm_100a kernels of libb200ddsp.so.
+
+    signal, hidden, (harmonic, noise) = model(units_frames, f0_frames, volume_frames,
+                                              spk_id=..., spk_mix_dict=..., initial_phase=..., infer=True)
+
+``unit2ctrl`` (the small network that predicts the frame-rate controls, reference
+ddsp/unit2control.py) is outside the accelerated path: pass your own module, or leave it None
+to use the reference's Unit2Control when the reference package is importable (the
+``patch_reference()`` drop-in scenario).
+
+Two noise modes: by default white noise is generated inside the FIR kernel (Philox, seeded
+from torch's CPU generator so ``torch.manual_seed`` makes runs reproducible); pass
+``noise=tensor [B, T]`` to feed explicit samples (parity tests feed what the reference's
+``rand_like`` drew).
+"""
+import torch
+
+from . import ops
+
+
+def _reference_unit2ctrl(n_unit, n_spk, split_map, **kw):
+    try:
+        from ddsp.unit2control import Unit2Control  # the reference's own class (not part of this repo)
+    except Exception as e:  # pragma: no cover - depends on the environment
+        raise RuntimeError(
+            "No unit2ctrl module was given and the reference's ddsp.unit2control.Unit2Control is not "
+            "importable; pass unit2ctrl=<module returning (controls dict, hidden)>.") from e
+    return Unit2Control(n_unit, n_spk, split_map, **kw)
+
+
+def _host_seed():
+    # consumes torch's CPU generator (reproducible under torch.manual_seed), no device sync
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+class _SynthBase(torch.nn.Module):
+    def _scalars(self):
+        """sampling_rate / block_size live in 0-dim buffers (state-dict compatible with the
+        reference, ddsp/vocoder.py:546-547); read them once, not on every call."""
+        c = self.__dict__.get("_scalar_cache")
+        if c is None:
+            c = (int(self.sampling_rate.item()), int(self.block_size.item()))
+            self.__dict__["_scalar_cache"] = c
+        return c
+
+    def _load_from_state_dict(self, *a, **k):
+        super()._load_from_state_dict(*a, **k)
+        self.__dict__["_scalar_cache"] = None
+
+    @staticmethod
+    def _forward_only(ctrls):
+        if torch.is_grad_enabled() and any(v.requires_grad for v in ctrls.values()):
+            raise NotImplementedError(
+                "the B200 synthesis kernels are forward-only; call under torch.no_grad() "
+                "(every inference caller of the reference does, e.g. main.py:250)")
+
+
+class Sins(_SynthBase):
+    """Sinusoids additive synthesiser -- reference ddsp/vocoder.py:532-611."""
+
+    def __init__(self, sampling_rate, block_size, n_harmonics, n_mag_allpass, n_mag_noise, n_unit=256, n_spk=1,
+                 unit2ctrl=None):
+        super().__init__()
+        self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
+        self.register_buffer("block_size", torch.tensor(block_size))
+        split_map = {
+            "amplitudes": n_harmonics,
+            "group_delay": n_mag_allpass,
+            "noise_magnitude": n_mag_noise,
+        }
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _reference_unit2ctrl(n_unit, n_spk, split_map)
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, initial_phase=None,
+                infer=True, max_upsample_dim=32, noise=None, utterance_offset=0):
+        """units_frames B x n_frames x n_unit; f0_frames B x n_frames x 1; volume_frames B x n_frames x 1.
+        ``max_upsample_dim`` only chunks the reference's temporaries and has no effect here."""
+        sr, block = self._scalars()
+        frame_phase, phase_frames = ops.phase_scan(f0_frames, block, sr, initial_phase, infer)
+        ctrls, hidden = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id=spk_id,
+                                       spk_mix_dict=spk_mix_dict)
+        self._forward_only(ctrls)
+        signal, harmonic, noise_out = ops.sins_synth(
+            f0_frames, frame_phase, ctrls["amplitudes"], ctrls["group_delay"], ctrls["noise_magnitude"], block, sr,
+            noise_in=noise, seed=0 if noise is not None else _host_seed(), utterance_offset=utterance_offset,
+            infer=infer)
+        return signal, hidden, (harmonic, noise_out)
+
+
+class FixedControls(torch.nn.Module):
+    """Stand-in for Unit2Control that returns preset raw controls: isolates the DSP path (the
+    seam the parity tests and the benchmark use; reference ddsp/vocoder.py:578)."""
+
+    def __init__(self, ctrls=None, hidden=None):
+        super().__init__()
+        self.ctrls, self.hidden = ctrls, hidden
+
+    def forward(self, units, f0, phase, volume, **kw):
+        self.last_phase_frames = phase
+        return self.ctrls, self.hidden

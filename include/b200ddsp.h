@@ -1,0 +1,138 @@
+/*
+ * b200ddsp.h -- C ABI of libb200ddsp.so: the B200 (sm_100a) DDSP harmonic-plus-noise
+ * synthesis kernels behind the reference's Sins / CombSub / CombSubSuperFast / SineGen
+ * forward() calls (yxlllc/DDSP-SVC).
+ *
+ * The reference has no FFI of its own: its "operator API" for this path is the Python
+ * module call (ddsp/vocoder.py:556,653,811; nsf_hifigan/models.py:150).  This header is
+ * what a maintainer binds (ctypes) to replace the tensor code inside
+ * those forward() methods.  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer to contiguous fp32 data unless
+ *    stated otherwise; `stream` is a cudaStream_t passed as void*.
+ *  - the library never allocates or frees device memory, never synchronises the stream
+ *    and keeps no mutable global state (thread-local last-error string only), so it is
+ *    re-entrant from any host thread (the reference is called from the audio-callback
+ *    thread of gui.py:376-414 and from Flask).
+ *  - return value: 0 = ok, <0 = argument error (B2D_ERR_*), >0 = cudaError_t of the failed
+ *    launch.  No exceptions or aborts cross the ABI.  b2d_last_error() describes the last
+ *    failure on the calling thread.
+ *  - "ctrl_stride": raw control tensors arrive as strided views of ONE dense
+ *    [B, n_frames, n_out] tensor (torch.split in ddsp/unit2control.py:12-23); every control
+ *    pointer therefore comes with the element stride between consecutive frames.
+ *  - T = n_frames * block.  Utterances (batch rows) are independent.
+ */
+#ifndef B200DDSP_H
+#define B200DDSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_VERSION 100
+
+#define B2D_ERR_NULL        (-1)  /* required pointer is NULL                         */
+#define B2D_ERR_SHAPE       (-2)  /* non-positive or inconsistent dimension           */
+#define B2D_ERR_ALIGN       (-3)  /* pointer / stride not aligned as required         */
+#define B2D_ERR_UNSUPPORTED (-4)  /* configuration outside what the kernels implement */
+#define B2D_ERR_WORKSPACE   (-5)  /* workspace too small                              */
+
+/* impulse-response construction modes (b2d_ir_build) */
+#define B2D_IR_ALLPASS      0  /* H = exp(j*cumsum(pi*tanh(c))), no window   (ddsp/vocoder.py:581,599) */
+#define B2D_IR_MAG_HANN     1  /* H = exp(c)/128, periodic Hann window        (ddsp/vocoder.py:582,606) */
+#define B2D_IR_MAG_DYNAMIC  2  /* H = exp(c), per-frame raised-cosine window  (ddsp/vocoder.py:835,849-851) */
+
+int         b2d_version(void);
+const char* b2d_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Exciter phase at frame rate.                       replaces ddsp/vocoder.py:564-575
+ * (same code at :743-753 and :819-829).
+ *   frame_phase[b,k] = sum_{i<k} (P f_i + (f_{i+1}-f_i)(P-1)/2)/sr  (+ initial_phase/2pi),
+ *                      unwrapped cycles, fp64  -- the closed form of the reference's
+ *                      per-sample fp64 cumsum of the linearly upsampled f0.
+ *   phase_frames[b,k] = 2*pi*fp32(wrap(x[k*P]))  -- the tensor handed to Unit2Control.
+ * f0_frames [B, n_frames] Hz.  initial_phase: NULL or [B] radians.
+ * round_fp32: 0 = infer=True (fp64 phase), 1 = infer=False (phase rounded to fp32 before
+ * wrapping, ddsp/vocoder.py:568).
+ */
+int b2d_phase_scan(const float* f0_frames, const float* initial_phase, int B, int n_frames,
+                   int block, double sampling_rate, int round_fp32,
+                   double* frame_phase, float* phase_frames, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Additive sinusoid bank.                            replaces ddsp/vocoder.py:580,585-594
+ * and ddsp/core.py:66-77 (upsample, remove_above_fmax).
+ *   sinusoids[b,t] = sum_{h=1..H} sin(h * phase[t]) * up(A)[t,h],
+ *   A[k,h] = exp(c_amp[k,h])/128 * (1[f0[k]*h < sr/2] + 1e-7).
+ * c_amp: raw 'amplitudes' control, [B, n_frames, H] with frame stride ctrl_stride.
+ */
+int b2d_sins_bank(const float* f0_frames, const double* frame_phase, const float* c_amp,
+                  int64_t ctrl_stride, int B, int n_frames, int block, int n_harmonics,
+                  double sampling_rate, int round_fp32, float* sinusoids, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Frame-wise impulse responses from raw controls.    replaces ddsp/core.py:254-270
+ * (frequency_impulse_response) + :185-237 / :240-251 (windows) and the activations at
+ * ddsp/vocoder.py:581-582,599,606,835-836,845,849-851.
+ *   ir[b,k,:] has L = 2*(n_mag-1) taps in causal form.
+ * dft_tables: device buffer of b2d_dft_tables_bytes(n_mag) bytes filled once by
+ * b2d_dft_tables() (constant cos/sin matrices of the L-point inverse real DFT).
+ * f0_frames is only read in mode B2D_IR_MAG_DYNAMIC (window half-width 1.5*sr/(f0+1e-3)).
+ */
+size_t b2d_dft_tables_bytes(int n_mag);
+int    b2d_dft_tables(int n_mag, float* dft_tables, void* stream);
+int    b2d_ir_build(const float* c, int64_t ctrl_stride, int mode, const float* f0_frames,
+                    const float* dft_tables, int B, int n_frames, int n_mag,
+                    double sampling_rate, float* ir, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Linear time-varying FIR (frequency_filter's convolution).   replaces ddsp/core.py:120-182
+ * (fft_convolve: Bartlett-windowed 50%-overlap frames, per-frame IR, overlap-add, crop
+ * with delay L/2).  Computed in direct form:
+ *   y[n] = sum_tau ((1-phi_m) h_f[tau] + phi_m h_{f+1}[tau]) x[m],  m = n + L/2 - tau,
+ *   f = floor(m/P), phi_m = (m mod P)/P, h_{nF} := h_{nF-1}, x = 0 outside [0,T).
+ * Up to two independent filters ("jobs") run in one launch and their outputs can be
+ * summed into `mix` (signal = harmonic + noise, ddsp/vocoder.py:609).
+ * x1 / x2: input [B, T]; NULL means "white noise U(-1,1) generated in-kernel" from
+ * Philox4x32-10 keyed by (seed, utterance index + utterance_offset, sample index)
+ * (replaces torch.rand_like(...)*2-1, ddsp/vocoder.py:603).
+ * y1 / y2 / mix may be NULL when that output is not wanted; job 2 is skipped when ir2 is
+ * NULL.
+ */
+int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1,
+                const float* x2, const float* ir2, int taps2, float* y2,
+                float* mix, uint64_t seed, int64_t utterance_offset,
+                int B, int n_frames, int block, void* stream);
+
+/* Same result by the plain one-thread-per-sample formula (any block size / tap count);
+ * used as the fallback for configurations the tiled kernel does not cover and as an
+ * on-device cross-check. One job only. */
+int b2d_ltv_fir_generic(const float* x, const float* ir, int taps, float* y,
+                        int B, int n_frames, int block, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Whole Sins synthesizer after Unit2Control.         replaces ddsp/vocoder.py:580-611
+ * Raw controls in, three waveforms out (any of signal/harmonic/noise_out may be NULL).
+ * noise_in: [B, T] uniform(-1,1) samples (parity mode) or NULL (in-kernel Philox).
+ * workspace: b2d_sins_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+size_t b2d_sins_workspace_bytes(int B, int n_frames, int block, int n_mag_allpass, int n_mag_noise);
+int    b2d_sins_synth(const float* f0_frames, const double* frame_phase,
+                      const float* c_amp, const float* c_group_delay, const float* c_noise,
+                      int64_t ctrl_stride, const float* noise_in, uint64_t seed,
+                      int64_t utterance_offset, const float* dft_tables_allpass,
+                      const float* dft_tables_noise, int B, int n_frames, int block,
+                      int n_harmonics, int n_mag_allpass, int n_mag_noise,
+                      double sampling_rate, int round_fp32,
+                      float* signal, float* harmonic, float* noise_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DDSP_H */
