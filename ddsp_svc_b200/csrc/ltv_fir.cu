@@ -51,12 +51,16 @@ struct FirParams {
     int nF, P, T;
 };
 
-__device__ __forceinline__ int swz(int q) {  // logical float index -> physical (16B-chunk XOR swizzle)
+// Input tile layout: the 2P samples are split into 16-byte chunks; even chunks live in `xe`, odd
+// chunks in `xo` (each P/4 float4).  A thread's window advances by one chunk per 4-tap step and
+// lanes are 2 chunks apart, so within one load instruction all lanes hit the SAME array at
+// consecutive float4 slots: conflict-free without any swizzle arithmetic, and with the loop
+// unrolled by 6 (3-register window rotation x even/odd alternation) every address is
+// pointer + immediate.
+__device__ __forceinline__ float x_at(const float4* xe, const float4* xo, int q) {
     const int c = q >> 2;
-    return ((c ^ ((c >> 3) & 1)) << 2) | (q & 3);
-}
-__device__ __forceinline__ float4 lds4(const float* xs, int chunk) {
-    return *reinterpret_cast<const float4*>(xs + ((chunk ^ ((chunk >> 3) & 1)) << 2));
+    const float4* arr = (c & 1) ? xo : xe;
+    return reinterpret_cast<const float*>(arr + (c >> 1))[q & 3];
 }
 
 __device__ __forceinline__ void fir_step(const float4& lo, const float4& mid, const float4& hi, const float4& t0,
@@ -75,11 +79,14 @@ __device__ __forceinline__ void fir_step(const float4& lo, const float4& mid, co
     }
 }
 
+// named barrier per job.  The id must be an immediate: with a register id ptxas reserves all 16
+// hardware barriers for the CTA, which caps residency at 4 CTAs/SM (measured).
 __device__ __forceinline__ void job_barrier(int job, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(job + 1), "r"(nthreads) : "memory");
+    if (job == 0) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory");
 }
 
-// threads per job = P/8.  smem per job: xs[2P] + tabA[2P] + pad[8] + tabB[2P]; then ybuf[2][P].
+// threads per job = P/8.  smem per job: xe[P] + xo[P] + tabA[2P] + pad[8] + tabB[2P]; then ybuf[2][P].
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
     extern __shared__ __align__(16) float sm[];
@@ -90,6 +97,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
     const int b = blockIdx.y, f = blockIdx.x;
     const int per_job = 6 * P + 8;
     float* xs = sm + job * per_job;
+    float4* xe = reinterpret_cast<float4*>(xs);
+    float4* xo = reinterpret_cast<float4*>(xs + P);
     float* tabA = xs + 2 * P;
     float* tabB = tabA + 2 * P + 8;
     float* ybuf = sm + p.njobs * per_job;  // [njobs][P]
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
                 if (xrow) v = __ldg(reinterpret_cast<const float4*>(xrow + m));
                 else v = b2d::philox_uniform_pm1(p.seed, (unsigned long long)(p.utt_off + b), (uint32_t)(m >> 2));
             }
-            *reinterpret_cast<float4*>(xs + ((c ^ ((c >> 3) & 1)) << 2)) = v;
+            ((c & 1) ? xo : xe)[c >> 1] = v;
         }
         // ---- tables for taps tau = sP + tau' ----
         const float* hm = irb + (size_t)min(max(g - 1, 0), nF - 1) * L;
@@ -135,54 +144,49 @@ __global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
             if (tau < L) { vm = __ldg(hm + tau); v0 = __ldg(h0 + tau); vp = __ldg(hp + tau); }
             const float w = (float)tp * invP;
             const float eA = vp - v0, eB = v0 - vm;
-            tabA[2 * tp] = fmaf(-w, eA, v0);
-            tabA[2 * tp + 1] = eA;
-            tabB[2 * tp] = fmaf(-w, eB, v0);
-            tabB[2 * tp + 1] = eB;
+            reinterpret_cast<float2*>(tabA)[tp] = make_float2(fmaf(-w, eA, v0), eA);
+            reinterpret_cast<float2*>(tabB)[tp] = make_float2(fmaf(-w, eB, v0), eB);
         }
         job_barrier(job, TPJ);
 
         // ---- main loop: P/4 steps of 4 taps ----
+        // step s loads chunk c0 - s with c0 = P/4 - 1 + 2 lt (odd): even steps read xo[k0 - s/2],
+        // odd steps read xe[k0 - (s-1)/2], k0 = P/8 - 1 + lt.
         const float4* tA = reinterpret_cast<const float4*>(tabA);
         const float4* tB = reinterpret_cast<const float4*>(tabB);
-        const int c0 = (P >> 2) - 1 + (lt << 1);  // chunk of logical q = P-4+i0
-        const int sw = lt << 1;                   // steps < sw use the A tables (tau0 < i0)
+        const int sw = lt << 1;  // steps < sw use the A tables (tau0 < i0)
         const int nsteps = P >> 2;
-        float4 A = lds4(xs, c0 + 1), Bv = lds4(xs, c0 + 2), C;
+        const float4* po = xo + ((P >> 3) - 1 + lt);
+        const float4* pe = xe + ((P >> 3) - 1 + lt);
+        float4 A = pe[1], Bv = po[1], C;  // chunks c0+1 (even) and c0+2 (odd)
         int step = 0;
-        for (; step + 3 <= nsteps; step += 3) {
-            {
-                const float4* tp4 = (step < sw) ? tA : tB;
-                const float4 t0 = tp4[2 * step], t1 = tp4[2 * step + 1];
-                C = lds4(xs, c0 - step);
-                fir_step(C, A, Bv, t0, t1, a1, a2);
-            }
-            {
-                const float4* tp4 = (step + 1 < sw) ? tA : tB;
-                const float4 t0 = tp4[2 * step + 2], t1 = tp4[2 * step + 3];
-                Bv = lds4(xs, c0 - step - 1);
-                fir_step(Bv, C, A, t0, t1, a1, a2);
-            }
-            {
-                const float4* tp4 = (step + 2 < sw) ? tA : tB;
-                const float4 t0 = tp4[2 * step + 4], t1 = tp4[2 * step + 5];
-                A = lds4(xs, c0 - step - 2);
-                fir_step(A, Bv, C, t0, t1, a1, a2);
-            }
+#define B2D_FIR_STEP(NEW, MID, HI, SRC, J)                                   \
+        {                                                                    \
+            const float4* tp4 = ((step + (J)) < sw ? tA : tB) + 2 * (step + (J)); \
+            const float4 t0 = tp4[0], t1 = tp4[1];                           \
+            NEW = (SRC);                                                     \
+            fir_step(NEW, MID, HI, t0, t1, a1, a2);                          \
         }
-        if (step < nsteps) {
-            const float4* tp4 = (step < sw) ? tA : tB;
-            const float4 t0 = tp4[2 * step], t1 = tp4[2 * step + 1];
-            C = lds4(xs, c0 - step);
-            fir_step(C, A, Bv, t0, t1, a1, a2);
-            ++step;
-            if (step < nsteps) {
-                const float4* tq4 = (step < sw) ? tA : tB;
-                const float4 u0 = tq4[2 * step], u1 = tq4[2 * step + 1];
-                Bv = lds4(xs, c0 - step);
-                fir_step(Bv, C, A, u0, u1, a1, a2);
-            }
+        for (; step + 6 <= nsteps; step += 6) {
+            B2D_FIR_STEP(C, A, Bv, po[0], 0)
+            B2D_FIR_STEP(Bv, C, A, pe[0], 1)
+            B2D_FIR_STEP(A, Bv, C, po[-1], 2)
+            B2D_FIR_STEP(C, A, Bv, pe[-1], 3)
+            B2D_FIR_STEP(Bv, C, A, po[-2], 4)
+            B2D_FIR_STEP(A, Bv, C, pe[-2], 5)
+            po -= 3;
+            pe -= 3;
         }
+        // remainder (nsteps mod 6 is even because nsteps is a multiple of 64): generic steps
+        for (; step < nsteps; step += 2) {
+            B2D_FIR_STEP(C, A, Bv, po[0], 0)
+            Bv = A; A = C;                       // window: (new, mid, hi) -> (mid, hi) of next step
+            B2D_FIR_STEP(C, A, Bv, pe[0], 1)
+            Bv = A; A = C;
+            po -= 1;
+            pe -= 1;
+        }
+#undef B2D_FIR_STEP
         // ---- band fix-up: taps tau' in [i0, i0+r) belong to the A tables for output r ----
 #pragma unroll
         for (int bb = 0; bb < 7; ++bb) {
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
             const float dE = tabA[2 * tp + 1] - tabB[2 * tp + 1];
 #pragma unroll
             for (int r = bb + 1; r < 8; ++r) {
-                const float xv = xs[swz(P - 1 + r - bb)];
+                const float xv = x_at(xe, xo, P - 1 + r - bb);
                 a1[r] = fmaf(xv, dG, a1[r]);
                 a2[r] = fmaf(xv, dE, a2[r]);
             }
@@ -308,6 +312,7 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "ltv_fir: smem attr: %s", cudaGetErrorString(e));
         }
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         kern<<<dim3(ntiles, B), threads, smem, st>>>(p);
         return check_launch("ltv_fir");
     };

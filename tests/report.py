@@ -12,10 +12,20 @@ def record(test, **metrics):
         os.makedirs(os.path.dirname(PATH), exist_ok=True)
         data = {}
         if os.path.isfile(PATH):
-            with open(PATH) as f:
-                data = json.load(f)
-        data[test] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in metrics.items()}
-        with open(PATH, "w") as f:
+            try:
+                with open(PATH) as f:
+                    data = json.load(f)
+            except Exception:
+                data = {}
+        def plain(v):
+            try:
+                return float(v)
+            except Exception:
+                return str(v)
+        data[test] = {k: plain(v) for k, v in metrics.items()}
+        tmp = PATH + ".tmp"
+        with open(tmp, "w") as f:
             json.dump(data, f, indent=1, sort_keys=True)
+        os.replace(tmp, PATH)
     except Exception:
         pass
