@@ -3,6 +3,7 @@ yxlllc/DDSP-SVC, behind the reference's Sins / CombSub / CombSubSuperFast / Sine
 API.  See DESIGN.md for the path, its boundary and the kernels; include/b200ddsp.h for the C ABI.
 """
 from . import _lib, ops, synthetic  # noqa: F401
-from .vocoder import FixedControls, Sins  # noqa: F401
+from .sinegen import SineGen  # noqa: F401
+from .vocoder import CombSub, FixedControls, Sins  # noqa: F401
 
-__all__ = ["Sins", "FixedControls", "ops", "synthetic"]
+__all__ = ["Sins", "CombSub", "SineGen", "FixedControls", "ops", "synthetic"]

@@ -184,3 +184,78 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
     _lib.check(rc, "b2d_sins_synth")
     _count(4 if Ma == Mn else 5)
     return signal, harmonic, noise
+
+
+def sinegen(f0, upp, sampling_rate, dim, rand_ini, sine_amp=0.1, noise_std=0.003, voiced_threshold=0.0,
+            noise_in=None, seed=0, utterance_offset=0):
+    """f0 [B, nF] -> [B, nF*upp, dim]  (reference nsf_hifigan/models.py:150-165)."""
+    _need_cuda_f32("f0", f0)
+    if f0.dim() != 2:
+        raise ValueError("f0 must be [B, n_frames]")
+    f0 = f0.contiguous()
+    B, nF = f0.shape
+    rand_ini = rand_ini.to(device=f0.device, dtype=torch.float32).reshape(-1).contiguous()
+    if rand_ini.numel() != dim:
+        raise ValueError("rand_ini must have %d elements" % dim)
+    if noise_in is not None:
+        _need_cuda_f32("noise_in", noise_in)
+        if tuple(noise_in.shape) != (B, nF * upp, dim):
+            raise ValueError("noise_in must be [B, n_frames*upp, dim]")
+        noise_in = noise_in.contiguous()
+    out = torch.empty(B, nF * upp, dim, dtype=torch.float32, device=f0.device)
+    ws = torch.empty(B, nF, dtype=torch.float32, device=f0.device)
+    rc = _lib.lib().b2d_sinegen(f0.data_ptr(), rand_ini.data_ptr(), _ptr(noise_in), int(seed), int(utterance_offset),
+                                B, nF, int(upp), int(dim), float(sampling_rate), float(sine_amp), float(noise_std),
+                                float(voiced_threshold), ws.data_ptr(), out.data_ptr(), _stream())
+    _lib.check(rc, "b2d_sinegen")
+    _count(2)
+    return out
+
+
+def comb_source(f0_frames, frame_phase, block, sampling_rate, infer=True):
+    f0 = _frames_2d(f0_frames)
+    B, nF = f0.shape
+    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    out = torch.empty(B, nF * block, dtype=torch.float32, device=f0.device)
+    rc = _lib.lib().b2d_comb_source(f0.data_ptr(), frame_phase.data_ptr(), B, nF, int(block), float(sampling_rate),
+                                    0 if infer else 1, out.data_ptr(), _stream())
+    _lib.check(rc, "b2d_comb_source")
+    _count(1)
+    return out
+
+
+def _same_stride(named, B, nF):
+    """Views of one dense control tensor share a frame stride; otherwise densify."""
+    views = [_ctrl_view(n, c, B, nF) for n, c in named]
+    if len({s for _, s in views}) == 1:
+        return [c for c, _ in views], views[0][1]
+    dense = torch.cat([c.contiguous() for c, _ in views], dim=-1)
+    parts = torch.split(dense, [c.shape[2] for c, _ in views], dim=-1)
+    return list(parts), dense.stride(1)
+
+
+def combsub_synth(f0_frames, frame_phase, c_group_delay, c_harmonic, c_noise, block, sampling_rate, noise_in=None,
+                  seed=0, utterance_offset=0, infer=True):
+    """Whole old-CombSub DSP after Unit2Control -> (signal, harmonic, noise) [B, T] each."""
+    f0 = _frames_2d(f0_frames)
+    B, nF = f0.shape
+    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    (cg, ch, cn), stride = _same_stride([("group_delay", c_group_delay), ("harmonic_magnitude", c_harmonic),
+                                         ("noise_magnitude", c_noise)], B, nF)
+    Ma, Mh, Mn = cg.shape[2], ch.shape[2], cn.shape[2]
+    dev, T = f0.device, nF * block
+    if noise_in is not None:
+        _need_cuda_f32("noise_in", noise_in)
+        noise_in = noise_in.reshape(B, T).contiguous()
+    L = _lib.lib()
+    ws_bytes = L.b2d_combsub_workspace_bytes(B, nF, int(block), Ma, Mh, Mn)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    signal, harmonic, noise = (torch.empty(B, T, dtype=torch.float32, device=dev) for _ in range(3))
+    rc = L.b2d_combsub_synth(f0.data_ptr(), frame_phase.data_ptr(), cg.data_ptr(), ch.data_ptr(), cn.data_ptr(),
+                             stride, _ptr(noise_in), int(seed), int(utterance_offset), dft_tables(Ma, dev).data_ptr(),
+                             dft_tables(Mh, dev).data_ptr(), dft_tables(Mn, dev).data_ptr(), B, nF, int(block), Ma,
+                             Mh, Mn, float(sampling_rate), 0 if infer else 1, signal.data_ptr(), harmonic.data_ptr(),
+                             noise.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    _lib.check(rc, "b2d_combsub_synth")
+    _count(6 if Ma == Mn else 7)
+    return signal, harmonic, noise

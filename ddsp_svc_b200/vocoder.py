@@ -88,6 +88,35 @@ class Sins(_SynthBase):
         return signal, hidden, (harmonic, noise_out)
 
 
+class CombSub(_SynthBase):
+    """Combtooth subtractive synthesiser (old version) -- reference ddsp/vocoder.py:788-862."""
+
+    def __init__(self, sampling_rate, block_size, n_mag_allpass, n_mag_harmonic, n_mag_noise, n_unit=256, n_spk=1,
+                 unit2ctrl=None):
+        super().__init__()
+        self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
+        self.register_buffer("block_size", torch.tensor(block_size))
+        split_map = {
+            "group_delay": n_mag_allpass,
+            "harmonic_magnitude": n_mag_harmonic,
+            "noise_magnitude": n_mag_noise,
+        }
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _reference_unit2ctrl(n_unit, n_spk, split_map)
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, initial_phase=None,
+                infer=True, noise=None, utterance_offset=0, **kwargs):
+        sr, block = self._scalars()
+        frame_phase, phase_frames = ops.phase_scan(f0_frames, block, sr, initial_phase, infer)
+        ctrls, hidden = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id=spk_id,
+                                       spk_mix_dict=spk_mix_dict)
+        self._forward_only(ctrls)
+        signal, harmonic, noise_out = ops.combsub_synth(
+            f0_frames, frame_phase, ctrls["group_delay"], ctrls["harmonic_magnitude"], ctrls["noise_magnitude"],
+            block, sr, noise_in=noise, seed=0 if noise is not None else _host_seed(),
+            utterance_offset=utterance_offset, infer=infer)
+        return signal, hidden, (harmonic, noise_out)
+
+
 class FixedControls(torch.nn.Module):
     """Stand-in for Unit2Control that returns preset raw controls: isolates the DSP path (the
     seam the parity tests and the benchmark use; reference ddsp/vocoder.py:578)."""

@@ -132,6 +132,45 @@ int    b2d_sins_synth(const float* f0_frames, const double* frame_phase,
                       float* signal, float* harmonic, float* noise_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * NSF-HiFiGAN SineGen f0 excitation.                 replaces nsf_hifigan/models.py:134-165
+ * (SineGen._f02sine + forward).  f0 [B, n_frames] (Hz, 0 = unvoiced), piecewise constant per
+ * frame of `upp` samples; out [B, n_frames*upp, dim], dim = harmonic_num + 1 <= 16.
+ * rand_ini [dim]: the random initial phases in cycles (element 0 = 0), drawn by the caller
+ * (reference: torch.rand(1,1,dim), models.py:144-145).
+ * noise_in [B, T, dim]: N(0,1) samples (parity mode) or NULL = in-kernel Philox + Box-Muller
+ * (replaces torch.randn_like, models.py:163).
+ * acc_workspace: B*n_frames floats (per-frame wrapped phase advance, models.py:139-141).
+ */
+int b2d_sinegen(const float* f0, const float* rand_ini, const float* noise_in, uint64_t seed,
+                int64_t utterance_offset, int B, int n_frames, int upp, int dim,
+                double sampling_rate, float sine_amp, float noise_std, float voiced_threshold,
+                float* acc_workspace, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CombSub (old version): comb-tooth source.          replaces ddsp/vocoder.py:819-829,839-840
+ *   comb[b,t] = sinc(sr * x[t] / (f0_up[t] + 1e-3)), x = wrapped phase (cycles, fp32).
+ */
+int b2d_comb_source(const float* f0_frames, const double* frame_phase, int B, int n_frames,
+                    int block, double sampling_rate, int round_fp32, float* comb, void* stream);
+
+/* Whole old-CombSub synthesizer after Unit2Control.  replaces ddsp/vocoder.py:834-862
+ * comb -> all-pass (group delay) -> harmonic magnitude filter with the per-frame dynamic
+ * window (half width 1.5*sr/(f0+1e-3)); noise -> Hann-windowed noise filter; signal = sum.
+ * signal/harmonic/noise_out may be NULL.  workspace: b2d_combsub_workspace_bytes bytes.
+ */
+size_t b2d_combsub_workspace_bytes(int B, int n_frames, int block, int n_mag_allpass,
+                                   int n_mag_harmonic, int n_mag_noise);
+int    b2d_combsub_synth(const float* f0_frames, const double* frame_phase,
+                         const float* c_group_delay, const float* c_harmonic, const float* c_noise,
+                         int64_t ctrl_stride, const float* noise_in, uint64_t seed,
+                         int64_t utterance_offset, const float* dft_tables_allpass,
+                         const float* dft_tables_harmonic, const float* dft_tables_noise,
+                         int B, int n_frames, int block, int n_mag_allpass, int n_mag_harmonic,
+                         int n_mag_noise, double sampling_rate, int round_fp32,
+                         float* signal, float* harmonic, float* noise_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

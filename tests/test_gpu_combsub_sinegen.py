@@ -1,0 +1,134 @@
+"""GPU parity of the old CombSub synthesizer and of SineGen against the live-reference goldens
+and the oracle, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from ddsp_svc_b200 import CombSub, FixedControls, SineGen, ops, synthetic as syn
+from tests import report, util
+from tests.golden import cases as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SR, P = G.SR, G.P
+OFFICIAL_RMS = 1e-4
+GATE_RMS = 2e-6
+
+
+def _dev_ctrls(inp):
+    return syn.split_views(inp["dense"].to(DEV), G.split_map(inp["case"]))
+
+
+@pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "combsub"])
+def test_combsub_stages(name):
+    inp = G.build_inputs(name)
+    ref = util.port_outputs(name, inp)
+    c = _dev_ctrls(inp)
+    f0 = inp["f0"].to(DEV)
+    fp, _ = ops.phase_scan(f0, P, SR)
+    comb = ops.comb_source(f0, fp, P, SR).cpu()
+    e_comb = util.rms(comb - ref["comb"])
+    ir_h = ops.ir_build(c["harmonic_magnitude"], ops.IR_MAG_DYNAMIC, SR, f0_frames=f0).cpu()
+    e_irh = (ir_h - ref["ir_harmonic"]).abs().max().item()
+    # 1022-tap FIR (two tap segments) on the oracle's intermediate signal
+    y = ops.ltv_fir(ref["allpassed"].to(DEV), ref["ir_harmonic"].to(DEV).contiguous(), P).cpu()
+    e_fir = util.rms(y - ref["harmonic"])
+    report.record("combsub_stages/" + name, comb_rms=e_comb, comb_max=(comb - ref["comb"]).abs().max().item(),
+                  ir_harmonic_max=e_irh, ir_harmonic_peak=ref["ir_harmonic"].abs().max().item(), fir1022_rms=e_fir,
+                  harmonic_rms=util.rms(ref["harmonic"]))
+    assert e_comb < 5e-6            # the reference's own fp32 comb sits ~1e-7 rms / 3e-6 max from exact math
+    assert e_irh < 2e-6 * max(1.0, ref["ir_harmonic"].abs().max().item())
+    assert e_fir < 1e-6
+
+
+@pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "combsub"])
+def test_combsub_forward_matches_reference_golden(name):
+    inp = G.build_inputs(name)
+    gold = util.load_golden(name)
+    case = inp["case"]
+    B, nF = case["B"], case["nF"]
+    hidden = torch.zeros(B, nF, 256, device=DEV)
+    model = CombSub(SR, P, case["Ma"], case["Mh"], case["Mn"], unit2ctrl=FixedControls(_dev_ctrls(inp), hidden)).to(DEV)
+    with torch.no_grad():
+        signal, hid, (harm, nz) = model(None, inp["f0"].to(DEV), None, noise=inp["noise"].to(DEV))
+    got = {"signal": signal.cpu().numpy(), "harmonic": harm.cpu().numpy(), "noise": nz.cpu().numpy()}
+    errs = {k: util.rms(got[k] - gold[k]) for k in got}
+    d = model.unit2ctrl.last_phase_frames.cpu().numpy() - gold["phase_frames"]
+    d = (d + np.pi) % (2 * np.pi) - np.pi
+    report.record("combsub_forward/" + name, signal_rms=util.rms(gold["signal"]), phase_frames_max=np.abs(d).max(),
+                  **{k + "_err": v for k, v in errs.items()})
+    assert np.abs(d).max() < 2e-6
+    for k, e in errs.items():
+        assert e < OFFICIAL_RMS and e < GATE_RMS, (k, e)
+    assert torch.equal(signal, harm + nz)
+
+
+def test_combsub_vs_float64_truth():
+    name = "combsub_b2_f24"
+    inp = G.build_inputs(name)
+    truth = util.closed_form_outputs(name, inp)
+    gold = util.load_golden(name)
+    c = _dev_ctrls(inp)
+    f0 = inp["f0"].to(DEV)
+    fp, _ = ops.phase_scan(f0, P, SR)
+    sig, _, _ = ops.combsub_synth(f0, fp, c["group_delay"], c["harmonic_magnitude"], c["noise_magnitude"], P, SR,
+                                  noise_in=inp["noise"].to(DEV))
+    e_gpu, e_ref = util.rms(sig.cpu().numpy() - truth["signal"]), util.rms(gold["signal"] - truth["signal"])
+    report.record("combsub_truth", gpu_vs_truth=e_gpu, reference_vs_truth=e_ref)
+    assert e_gpu < 1e-6
+
+
+@pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "sinegen"])
+def test_sinegen_matches_reference_golden(name):
+    inp = G.build_inputs(name)
+    gold = util.load_golden(name)
+    case = inp["case"]
+    gen = SineGen(SR, harmonic_num=case["harmonic_num"])
+    out = gen(inp["f0"].to(DEV), case["upp"], rand_ini=inp["rand_ini"].to(DEV), noise=inp["noise"].to(DEV)).cpu().numpy()
+    assert out.shape == gold["out"].shape
+    e, m = util.rms(out - gold["out"]), np.abs(out - gold["out"]).max()
+    report.record("sinegen/" + name, rms=e, max=m, ref_rms=util.rms(gold["out"]))
+    assert e < OFFICIAL_RMS and e < GATE_RMS
+    assert m < 2e-5
+
+
+def test_sinegen_in_kernel_noise():
+    """Throughput mode: Gaussian noise from Philox + Box-Muller inside the kernel."""
+    B, nF, upp, dim = 3, 40, 512, 9
+    gen = SineGen(SR, harmonic_num=dim - 1)
+    f0 = torch.zeros(B, nF, device=DEV)          # all unvoiced: out = (sine_amp/3) * eps
+    torch.manual_seed(5)
+    a = gen(f0, upp)
+    torch.manual_seed(5)
+    b = gen(f0, upp)
+    assert torch.equal(a, b)
+    eps = (a / (0.1 / 3)).double().cpu().numpy()
+    report.record("sinegen_noise", mean=eps.mean(), var=eps.var(), kurt=((eps - eps.mean()) ** 4).mean() / eps.var() ** 2)
+    assert abs(eps.mean()) < 5e-3 and abs(eps.var() - 1) < 1e-2
+    assert abs(((eps - eps.mean()) ** 4).mean() / eps.var() ** 2 - 3) < 0.05
+    assert abs(np.corrcoef(eps[0, :, 0], eps[0, :, 1])[0, 1]) < 0.02
+    assert abs(np.corrcoef(eps[0, :-1, 3], eps[0, 1:, 3])[0, 1]) < 0.02
+    # voiced part: deterministic sines + small noise; shard invariance of the noise stream
+    f0v = syn.make_f0(B, nF, SR, upp)[..., 0].to(DEV)
+    ri = torch.zeros(dim)
+    x = ops.sinegen(f0v, upp, SR, dim, ri, seed=9)
+    y = ops.sinegen(f0v[1:], upp, SR, dim, ri, seed=9, utterance_offset=1)
+    assert torch.equal(x[1:], y)
+
+
+def test_sinegen_full_size_config5():
+    """BASELINE config 5 shape: B=64 x 10 s x 9 harmonics (1 GB output)."""
+    B, nF, upp, dim = 64, 861, 512, 9
+    f0 = syn.make_f0(B, nF, SR, upp, unvoiced_fraction=0.1)[..., 0]
+    ri = torch.rand(dim); ri[0] = 0
+    out = ops.sinegen(f0.to(DEV), upp, SR, dim, ri, seed=3)
+    assert out.shape == (B, nF * upp, dim) and torch.isfinite(out).all()
+    # one utterance against the oracle with its noise removed: feed zeros as noise
+    from oracle import torch_port as tp
+    row = 11
+    z = torch.zeros(1, nF * upp, dim)
+    ref = tp.sinegen_forward(f0[row:row + 1], upp, SR, dim - 1, rand_ini=ri.reshape(1, 1, -1), noise=z)["out"]
+    got = ops.sinegen(f0[row:row + 1].to(DEV), upp, SR, dim, ri, noise_in=z.to(DEV)).cpu()
+    e = util.rms(got - ref)
+    report.record("sinegen_full", row_rms=e, row_max=(got - ref).abs().max().item())
+    assert e < GATE_RMS
