@@ -4,6 +4,6 @@ API.  See DESIGN.md for the path, its boundary and the kernels; include/b200ddsp
 """
 from . import _lib, ops, synthetic  # noqa: F401
 from .sinegen import SineGen  # noqa: F401
-from .vocoder import CombSub, FixedControls, Sins  # noqa: F401
+from .vocoder import CombSub, CombSubSuperFast, FixedControls, Sins  # noqa: F401
 
-__all__ = ["Sins", "CombSub", "SineGen", "FixedControls", "ops", "synthetic"]
+__all__ = ["Sins", "CombSub", "CombSubSuperFast", "SineGen", "FixedControls", "ops", "synthetic"]

@@ -259,3 +259,36 @@ def combsub_synth(f0_frames, frame_phase, c_group_delay, c_harmonic, c_noise, bl
     _lib.check(rc, "b2d_combsub_synth")
     _count(6 if Ma == Mn else 7)
     return signal, harmonic, noise
+
+
+def superfast_scan(f0_frames, block, sampling_rate):
+    """-> (workspace tensor holding per-frame source parameters, phase_frames [B, nF, 1])."""
+    f0 = _frames_2d(f0_frames)
+    B, nF = f0.shape
+    L = _lib.lib()
+    ws = torch.empty(L.b2d_superfast_workspace_bytes(B, nF), dtype=torch.uint8, device=f0.device)
+    phase_frames = torch.empty(B, nF, 1, dtype=torch.float32, device=f0.device)
+    rc = L.b2d_superfast_scan(f0.data_ptr(), B, nF, int(block), float(sampling_rate), ws.data_ptr(),
+                              phase_frames.data_ptr(), _stream())
+    _lib.check(rc, "b2d_superfast_scan")
+    _count(1)
+    return ws, phase_frames
+
+
+def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None, seed=0, utterance_offset=0):
+    B, nF = c_hm.shape[0], c_hm.shape[1]
+    (hm, hp, nm, npz), stride = _same_stride([("harmonic_magnitude", c_hm), ("harmonic_phase", c_hp),
+                                              ("noise_magnitude", c_nm), ("noise_phase", c_np)], B, nF)
+    if hm.shape[2] != win_length // 2 + 1:
+        raise ValueError("controls must have win_length/2+1 = %d bins" % (win_length // 2 + 1))
+    T = nF * block
+    if noise_in is not None:
+        _need_cuda_f32("noise_in", noise_in)
+        noise_in = noise_in.reshape(B, T).contiguous()
+    signal = torch.empty(B, T, dtype=torch.float32, device=hm.device)
+    rc = _lib.lib().b2d_superfast_synth(ws.data_ptr(), hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), npz.data_ptr(),
+                                        stride, _ptr(noise_in), int(seed), int(utterance_offset), B, nF, int(block),
+                                        int(win_length), signal.data_ptr(), _stream())
+    _lib.check(rc, "b2d_superfast_synth")
+    _count(1)
+    return signal

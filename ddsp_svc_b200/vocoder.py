@@ -117,6 +117,49 @@ class CombSub(_SynthBase):
         return signal, hidden, (harmonic, noise_out)
 
 
+class CombSubSuperFast(_SynthBase):
+    """Combtooth subtractive synthesiser (STFT-domain filtering; what configs/combsub.yaml
+    selects) -- reference ddsp/vocoder.py:613-710.  Returns (signal, hidden, (signal, signal))
+    with the same tensor three times, like the reference."""
+
+    def __init__(self, sampling_rate, block_size, win_length, n_unit=256, n_spk=1, use_pitch_aug=False,
+                 pcmer_norm=False, unit2ctrl=None):
+        super().__init__()
+        self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
+        self.register_buffer("block_size", torch.tensor(block_size))
+        self.register_buffer("win_length", torch.tensor(win_length))
+        self.register_buffer("window", torch.hann_window(win_length))
+        split_map = {
+            "harmonic_magnitude": win_length // 2 + 1,
+            "harmonic_phase": win_length // 2 + 1,
+            "noise_magnitude": win_length // 2 + 1,
+            "noise_phase": win_length // 2 + 1,
+        }
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _reference_unit2ctrl(
+            n_unit, n_spk, split_map, use_pitch_aug=use_pitch_aug, use_naive_v2=True, use_conv_stack=True)
+
+    def _scalars(self):
+        c = self.__dict__.get("_scalar_cache")
+        if c is None:
+            c = (int(self.sampling_rate.item()), int(self.block_size.item()), int(self.win_length.item()))
+            self.__dict__["_scalar_cache"] = c
+        return c
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, aug_shift=None,
+                initial_phase=None, infer=True, noise=None, utterance_offset=0, **kwargs):
+        """``initial_phase`` is accepted and ignored, like the reference (ddsp/vocoder.py:653-661)."""
+        sr, block, win = self._scalars()
+        ws, phase_frames = ops.superfast_scan(f0_frames, block, sr)
+        ctrls, hidden = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id=spk_id,
+                                       spk_mix_dict=spk_mix_dict, aug_shift=aug_shift)
+        self._forward_only(ctrls)
+        signal = ops.superfast_synth(ws, ctrls["harmonic_magnitude"], ctrls["harmonic_phase"],
+                                     ctrls["noise_magnitude"], ctrls["noise_phase"], block, win, noise_in=noise,
+                                     seed=0 if noise is not None else _host_seed(),
+                                     utterance_offset=utterance_offset)
+        return signal, hidden, (signal, signal)
+
+
 class FixedControls(torch.nn.Module):
     """Stand-in for Unit2Control that returns preset raw controls: isolates the DSP path (the
     seam the parity tests and the benchmark use; reference ddsp/vocoder.py:578)."""

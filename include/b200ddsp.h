@@ -171,6 +171,28 @@ int    b2d_combsub_synth(const float* f0_frames, const double* frame_phase,
                          float* signal, float* harmonic, float* noise_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * CombSubSuperFast (what configs/combsub.yaml selects).   replaces ddsp/vocoder.py:639-710
+ * Two steps around Unit2Control, like the reference:
+ *  b2d_superfast_scan : per-frame source parameters (s, ds, wrapped phase advance) into
+ *                       `workspace` (b2d_superfast_workspace_bytes) and phase_frames [B,nF]
+ *                       = 2*pi*rad[:, :, 0]                      (fast_source_gen, :639-651)
+ *  b2d_superfast_synth: comb source -> STFT (2048/512, Hann, reflect) of comb and of N(0,1)
+ *                       noise -> Y = X exp(m_h + j pi p_h) + N exp(m_n + j pi p_n)/128 (last
+ *                       frame repeated) -> iSTFT -> signal [B, n_frames*block]   (:666-708)
+ * The four raw controls [B, n_frames, win_length/2+1] share ctrl_stride.
+ * noise_in [B,T] N(0,1) (parity) or NULL (in-kernel Philox + Box-Muller).
+ * Only win_length = 2048, block = 512 is implemented (B2D_ERR_UNSUPPORTED otherwise).
+ */
+size_t b2d_superfast_workspace_bytes(int B, int n_frames);
+int    b2d_superfast_scan(const float* f0_frames, int B, int n_frames, int block,
+                          double sampling_rate, void* workspace, float* phase_frames, void* stream);
+int    b2d_superfast_synth(const void* workspace, const float* c_harmonic_magnitude,
+                           const float* c_harmonic_phase, const float* c_noise_magnitude,
+                           const float* c_noise_phase, int64_t ctrl_stride, const float* noise_in,
+                           uint64_t seed, int64_t utterance_offset, int B, int n_frames, int block,
+                           int win_length, float* signal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
