@@ -30,6 +30,12 @@ WORKLOADS = {
                  label="Sins forward DSP, B=32 x 10 s x 128 harmonics, 44.1 kHz, n_mag 256/256 (BASELINE configs[1])"),
     "sins_cfg1": dict(kind="sins", B=1, sec=2, H=64, Ma=256, Mn=256,
                       label="Sins forward DSP, B=1 x 2 s x 64 harmonics (BASELINE configs[0])"),
+    "combsub": dict(kind="combsub", B=32, sec=10, Ma=256, Mh=512, Mn=256,
+                    label="CombSub (old) forward DSP, B=32 x 10 s, n_mag 256/512/256 (BASELINE configs[2], class CombSub)"),
+    "superfast": dict(kind="superfast", B=32, sec=10, win=2048,
+                      label="CombSubSuperFast forward DSP (configs/combsub.yaml), B=32 x 10 s, win 2048 (BASELINE configs[2])"),
+    "sinegen": dict(kind="sinegen", B=64, sec=10, dim=9,
+                    label="nsf_hifigan SineGen, B=64 x 10 s, 9 harmonics (BASELINE configs[4])"),
 }
 
 
@@ -40,7 +46,39 @@ def algorithmic_bytes(w, nF):
     if w["kind"] == "sins":
         c = w["H"] + w["Ma"] + w["Mn"]
         return 4 * B * nF * (1 + c) + 4 * B * T * 3
+    if w["kind"] == "combsub":
+        c = w["Ma"] + w["Mh"] + w["Mn"]
+        return 4 * B * nF * (1 + c) + 4 * B * T * 3
+    if w["kind"] == "superfast":
+        return 4 * B * nF * (1 + 4 * (w["win"] // 2 + 1)) + 4 * B * T
+    if w["kind"] == "sinegen":
+        return 4 * B * nF + 4 * B * T * w["dim"]
     raise ValueError(w["kind"])
+
+
+def split_map_of(w):
+    from ddsp_svc_b200 import synthetic as syn
+    k = w["kind"]
+    if k == "sins":
+        return syn.sins_split_map(w["H"], w["Ma"], w["Mn"])
+    if k == "combsub":
+        return syn.combsub_split_map(w["Ma"], w["Mh"], w["Mn"])
+    if k == "superfast":
+        return syn.superfast_split_map(w["win"])
+    return None
+
+
+def oracle_forward(w, f0, ctrls):
+    """The reference's CPU algorithm (oracle port) for one workload kind."""
+    from oracle import torch_port as tp
+    k = w["kind"]
+    if k == "sins":
+        return tp.sins_forward(f0, ctrls, SR, P)
+    if k == "combsub":
+        return tp.combsub_forward(f0, ctrls, SR, P)
+    if k == "superfast":
+        return tp.superfast_forward(f0, ctrls, SR, P, w["win"])
+    return tp.sinegen_forward(f0[..., 0], P, SR, w["dim"] - 1)
 
 
 # ------------------------------------------------------------------------------------------
@@ -108,15 +146,15 @@ def cpu_reference_run(w, batch, reps, threads=None):
     cores = threads or best_thread_count(w)
     torch.set_num_threads(cores)
     nF = syn.n_frames_for(w["sec"], SR, P)
-    sm = syn.sins_split_map(w["H"], w["Ma"], w["Mn"])
+    sm = split_map_of(w)
     f0 = syn.make_f0(batch, nF, SR, P)
-    _, ctrls = syn.make_ctrl(batch, nF, sm)
+    ctrls = syn.make_ctrl(batch, nF, sm)[1] if sm else None
     best = None
     with torch.no_grad():
-        tp.sins_forward(f0[:1], {k: v[:1] for k, v in ctrls.items()}, SR, P)  # warm-up (small)
+        oracle_forward(w, f0[:1], {k: v[:1] for k, v in ctrls.items()} if ctrls else None)  # warm-up (small)
         for _ in range(reps):
             t0 = time.perf_counter()
-            tp.sins_forward(f0, ctrls, SR, P)
+            oracle_forward(w, f0, ctrls)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     return batch * nF * P / best / 1e6, best, cores
@@ -137,21 +175,25 @@ def best_thread_count(w):
         return _best_threads[key]
     ncpu = os.cpu_count() or 1
     nF = syn.n_frames_for(min(w["sec"], 2), SR, P)
-    sm = syn.sins_split_map(w["H"], w["Ma"], w["Mn"])
+    sm = split_map_of(w)
     f0 = syn.make_f0(2, nF, SR, P)
-    _, ctrls = syn.make_ctrl(2, nF, sm)
+    ctrls = syn.make_ctrl(2, nF, sm)[1] if sm else None
     best, best_t = ncpu, None
     for n in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
         torch.set_num_threads(n)
         with torch.no_grad():
-            tp.sins_forward(f0, ctrls, SR, P)
+            oracle_forward(w, f0, ctrls)
             t0 = time.perf_counter()
-            tp.sins_forward(f0, ctrls, SR, P)
+            oracle_forward(w, f0, ctrls)
             dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = n, dt
     _best_threads[key] = best
     return best
+
+
+def metric_name(w):
+    return "audio Msamples/s (44.1 kHz, %s)" % ("%d harmonics" % w["H"] if "H" in w else w["kind"])
 
 
 def run_reference_arm(args, w):
@@ -173,7 +215,7 @@ def run_reference_arm(args, w):
         vals.append(v); t_total += dt
     value = sample_b * nF * P * args.steps / t_total / 1e6
     sample = "%d of %d utterances x %d s per step (bounded sample of the same workload)" % (sample_b, w["B"], w["sec"])
-    line = {"impl": "reference", "metric": "audio Msamples/s (44.1 kHz, %d harmonics)" % w["H"], "value": value,
+    line = {"impl": "reference", "metric": metric_name(w), "value": value,
             "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -185,6 +227,98 @@ def run_reference_arm(args, w):
 
 
 # ------------------------------------------------------------------------------------------
+class Runner:
+    """Per-workload device state: how to run one step and how to time each kernel alone."""
+
+    def __init__(self, w, dev, rank, torch):
+        from ddsp_svc_b200 import CombSub, CombSubSuperFast, FixedControls, SineGen, Sins, ops, synthetic as syn
+        self.w, self.dev, self.rank, self.torch, self.ops, self.syn = w, dev, rank, torch, ops, syn
+        B = self.B = w["B"]
+        nF = self.nF = syn.n_frames_for(w["sec"], SR, P)
+        self.T = nF * P
+        self.sm = split_map_of(w)
+        self.f0_h = syn.make_f0(B, nF, SR, P, seed=1234 + rank).pin_memory()
+        self.f0_d = self.f0_h.to(dev)
+        self.h2d = self.f0_h.numel() * 4
+        k = w["kind"]
+        if k == "sinegen":
+            self.rand_ini = torch.rand(w["dim"]); self.rand_ini[0] = 0
+            self.model = SineGen(SR, harmonic_num=w["dim"] - 1)
+            self.out_h = torch.empty(B, self.T, w["dim"], dtype=torch.float32).pin_memory()
+            return
+        self.dense_h = syn.make_ctrl(B, nF, self.sm, seed=7 + rank)[0].pin_memory()
+        self.dense_d = self.dense_h.to(dev)
+        self.ctrl_d = syn.split_views(self.dense_d, self.sm)
+        self.h2d += self.dense_h.numel() * 4
+        self.fixed = FixedControls(self.ctrl_d, torch.zeros(B, nF, 256, device=dev))
+        if k == "sins":
+            self.model = Sins(SR, P, w["H"], w["Ma"], w["Mn"], unit2ctrl=self.fixed).to(dev)
+        elif k == "combsub":
+            self.model = CombSub(SR, P, w["Ma"], w["Mh"], w["Mn"], unit2ctrl=self.fixed).to(dev)
+        else:
+            self.model = CombSubSuperFast(SR, P, w["win"], unit2ctrl=self.fixed).to(dev)
+        self.out_h = torch.empty(B, self.T, dtype=torch.float32).pin_memory()
+
+    # one pass of the hot path with inputs resident in HBM; returns the waveform to gather
+    def step(self, f0=None):
+        f0 = self.f0_d if f0 is None else f0
+        if self.w["kind"] == "sinegen":
+            return self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B)
+        return self.model(None, f0, None, utterance_offset=self.rank * self.B)[0]
+
+    # the same through HOST buffers: pinned inputs -> H2D -> public module API -> D2H of the result
+    def step_e2e(self):
+        f0_x = self.f0_h.to(self.dev, non_blocking=True)
+        if self.w["kind"] != "sinegen":
+            self.fixed.ctrls = self.syn.split_views(self.dense_h.to(self.dev, non_blocking=True), self.sm)
+        sig = self.step(f0_x)
+        self.out_h.copy_(sig, non_blocking=True)
+        if self.w["kind"] != "sinegen":
+            self.fixed.ctrls = self.ctrl_d
+
+    def kernels(self):
+        """name -> callable launching exactly that kernel (inputs prepared beforehand)."""
+        ops, w, c, f0, B, nF, T = self.ops, self.w, getattr(self, "ctrl_d", None), self.f0_d, self.B, self.nF, self.T
+        torch, dev = self.torch, self.dev
+        L = ops._lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        k = w["kind"]
+        if k == "sinegen":
+            return {"sinegen(scan+stream)": lambda: ops.sinegen(f0[..., 0], P, SR, w["dim"], self.rand_ini, seed=1)}
+        if k == "superfast":
+            ws, _ = ops.superfast_scan(f0, P, SR)
+            return {"superfast_scan": lambda: ops.superfast_scan(f0, P, SR),
+                    "superfast_kernel": lambda: ops.superfast_synth(ws, c["harmonic_magnitude"], c["harmonic_phase"],
+                                                                    c["noise_magnitude"], c["noise_phase"], P, w["win"], seed=1)}
+        fp, _ = ops.phase_scan(f0, P, SR)
+        buf = [torch.empty(B, T, device=dev) for _ in range(3)]
+        if k == "sins":
+            sinus = ops.sins_bank(f0, fp, c["amplitudes"], P, SR)
+            ir_a = ops.ir_build(c["group_delay"], ops.IR_ALLPASS, SR)
+            ir_n = ops.ir_build(c["noise_magnitude"], ops.IR_MAG_HANN, SR)
+            La, Ln = ir_a.shape[2], ir_n.shape[2]
+            return {"phase_scan": lambda: ops.phase_scan(f0, P, SR),
+                    "sins_bank": lambda: ops.sins_bank(f0, fp, c["amplitudes"], P, SR),
+                    "ir_build_allpass": lambda: ops.ir_build(c["group_delay"], ops.IR_ALLPASS, SR),
+                    "ir_build_noise": lambda: ops.ir_build(c["noise_magnitude"], ops.IR_MAG_HANN, SR),
+                    "ltv_fir_x2_mix": lambda: L.b2d_ltv_fir(sinus.data_ptr(), ir_a.data_ptr(), La, buf[0].data_ptr(), 0,
+                                                            ir_n.data_ptr(), Ln, buf[1].data_ptr(), buf[2].data_ptr(),
+                                                            1, 0, B, nF, P, st)}
+        comb = ops.comb_source(f0, fp, P, SR)
+        ir_a = ops.ir_build(c["group_delay"], ops.IR_ALLPASS, SR)
+        ir_h = ops.ir_build(c["harmonic_magnitude"], ops.IR_MAG_DYNAMIC, SR, f0_frames=f0)
+        ir_n = ops.ir_build(c["noise_magnitude"], ops.IR_MAG_HANN, SR)
+        return {"phase_scan": lambda: ops.phase_scan(f0, P, SR),
+                "comb_source": lambda: ops.comb_source(f0, fp, P, SR),
+                "ir_build_allpass": lambda: ops.ir_build(c["group_delay"], ops.IR_ALLPASS, SR),
+                "ir_build_dynamic": lambda: ops.ir_build(c["harmonic_magnitude"], ops.IR_MAG_DYNAMIC, SR, f0_frames=f0),
+                "ir_build_noise": lambda: ops.ir_build(c["noise_magnitude"], ops.IR_MAG_HANN, SR),
+                "ltv_fir_allpass+noise": lambda: L.b2d_ltv_fir(comb.data_ptr(), ir_a.data_ptr(), ir_a.shape[2],
+                                                               buf[0].data_ptr(), 0, ir_n.data_ptr(), ir_n.shape[2],
+                                                               buf[1].data_ptr(), 0, 1, 0, B, nF, P, st),
+                "ltv_fir_harmonic_1022": lambda: ops.ltv_fir(comb, ir_h, P)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +327,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sins", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the waveform")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -202,7 +337,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from ddsp_svc_b200 import FixedControls, Sins, ops, synthetic as syn
+    from ddsp_svc_b200 import ops, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,28 +350,15 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = w["B"]
-    nF = syn.n_frames_for(w["sec"], SR, P)
-    T = nF * P
-    sm = syn.sins_split_map(w["H"], w["Ma"], w["Mn"])
-    # per-rank shard of the global batch: utterances [rank*B, (rank+1)*B)
-    f0_h = syn.make_f0(B, nF, SR, P, seed=1234 + rank).pin_memory()
-    dense_h, _ = syn.make_ctrl(B, nF, sm, seed=7 + rank)
-    dense_h = dense_h.pin_memory()
-    f0_d = f0_h.to(dev)
-    dense_d = dense_h.to(dev)
-    ctrl_d = syn.split_views(dense_d, sm)
-    hidden = torch.zeros(B, nF, 256, device=dev)
-    fixed = FixedControls(ctrl_d, hidden)
-    model = Sins(SR, P, w["H"], w["Ma"], w["Mn"], unit2ctrl=fixed).to(dev)
-    gathered = torch.empty(world * B, T, device=dev) if (world > 1 and rank == 0) else None
+    run = Runner(w, dev, rank, torch)
+    B, nF, T = run.B, run.nF, run.T
+    do_gather = world > 1 and not args.no_gather
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    out_h = torch.empty(B, T, dtype=torch.float32).pin_memory()
 
     def step():
-        sig, _, (harm, nz) = model(None, f0_d, None, utterance_offset=rank * B)
-        if world > 1:
-            dist.gather(sig, list(gathered.split(B)) if rank == 0 else None, dst=0)
+        sig = run.step()
+        if do_gather:
+            sharding.gather_waveform(sig.reshape(B, -1), world * B, dst=0)
         return sig
 
     def sync_all():
@@ -267,39 +389,23 @@ def main():
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
         # ---- end to end through the public module API with HOST buffers ----
-        e2e_steps = max(3, min(args.steps, 10))
-        h2d = f0_h.numel() * 4 + dense_h.numel() * 4
-        d2h = out_h.numel() * 4
         ee = []
-        for i in range(e2e_steps + 1):
+        for i in range(max(3, min(args.steps, 10)) + 1):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            f0_x = f0_h.to(dev, non_blocking=True)
-            dn_x = dense_h.to(dev, non_blocking=True)
-            fixed.ctrls = syn.split_views(dn_x, sm)
-            sig, _, _ = model(None, f0_x, None, utterance_offset=rank * B)
-            out_h.copy_(sig, non_blocking=True)
+            run.step_e2e()
             b.record()
             b.synchronize()
             if i > 0:
                 ee.append(a.elapsed_time(b))
-        fixed.ctrls = ctrl_d
         e2e_ms = sum(ee) / len(ee)
         clk = clocks.stop() if rank == 0 else None
 
         # ---- per-kernel durations (CUDA events on the launching stream), for the roofline ----
         kt = {}
         reps = max(5, min(args.steps, 20))
-        fp, _ = ops.phase_scan(f0_d, P, SR)
-        sinus = ops.sins_bank(f0_d, fp, ctrl_d["amplitudes"], P, SR)
-        ir_a = ops.ir_build(ctrl_d["group_delay"], ops.IR_ALLPASS, SR)
-        ir_n = ops.ir_build(ctrl_d["noise_magnitude"], ops.IR_MAG_HANN, SR)
-        L = ops._lib.lib()
-        sig_b, har_b, nz_b = (torch.empty(B, T, device=dev) for _ in range(3))
-        st = torch.cuda.current_stream().cuda_stream
-
-        def timed(name, fn):
+        for name, fn in run.kernels().items():
             ts = []
             for _ in range(reps):
                 flush.zero_()
@@ -307,14 +413,6 @@ def main():
                 a.record(); fn(); b.record(); b.synchronize()
                 ts.append(a.elapsed_time(b))
             kt[name] = sum(ts) / len(ts)
-
-        timed("phase_scan", lambda: ops.phase_scan(f0_d, P, SR))
-        timed("sins_bank", lambda: ops.sins_bank(f0_d, fp, ctrl_d["amplitudes"], P, SR))
-        timed("ir_build_allpass", lambda: ops.ir_build(ctrl_d["group_delay"], ops.IR_ALLPASS, SR))
-        timed("ir_build_noise", lambda: ops.ir_build(ctrl_d["noise_magnitude"], ops.IR_MAG_HANN, SR))
-        timed("ltv_fir_x2_mix", lambda: L.b2d_ltv_fir(sinus.data_ptr(), ir_a.data_ptr(), 510, har_b.data_ptr(), 0,
-                                                      ir_n.data_ptr(), 510, nz_b.data_ptr(), sig_b.data_ptr(), 1, 0,
-                                                      B, nF, P, st))
 
     # ---- reduce over ranks: max device time ----
     if world > 1:
@@ -331,30 +429,31 @@ def main():
         alg_bytes = algorithmic_bytes(w, nF)
         achieved = alg_bytes / (kt[dom] * 1e-3) / 1e9
         line = {
-            "metric": "audio Msamples/s (44.1 kHz, %d harmonics)" % w["H"],
+            "metric": metric_name(w),
             "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "per_gpu_batch": B, "global_batch": world * B, "n_frames": nF,
                        "samples_per_utterance": T, "noise": "in-kernel Philox4x32-10",
-                       "outputs": "signal+harmonic+noise", "parallelism": "batch-sharded x%d%s" % (
-                           world, ", NCCL gather of signal to rank 0 inside the step" if world > 1 else ""),
+                       "outputs": "signal+harmonic+noise" if w["kind"] in ("sins", "combsub") else "signal",
+                       "parallelism": "batch-sharded x%d%s" % (
+                           world, ", NCCL gather of the waveform to rank 0 inside the step" if do_gather else ""),
                        "l2": "flushed between steps (256 MiB memset, untimed); per-step CUDA events summed",
                        "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt,
                          "whole_path_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None,
-                         "note": "Sins is FP32/SFU-issue bound (2040 FMA + 70 MUFU per sample against 17 B); "
-                                 "see DESIGN.md for the pipe-utilisation view"},
+                         "note": "achieved = algorithmic bytes of the whole path / duration of the dominant kernel; "
+                                 "Sins/CombSub are FP32/SFU-issue bound by construction (see DESIGN.md)"},
             "e2e": {"value": samples_step / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "pinned host f0+controls -> H2D -> Sins.forward (public module API) -> D2H of signal"},
+                    "h2d_bytes_per_step": run.h2d, "d2h_bytes_per_step": run.out_h.numel() * 4,
+                    "what": "pinned host f0+controls -> H2D -> module forward (public API) -> D2H of the waveform"},
             "gpu_launches": launches,
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            sample_b = 4
+            sample_b = 4 if w["B"] >= 4 else w["B"]
             v, dt, cores = cpu_reference_run(w, sample_b, 3)
             line["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                     "sample": "%d of %d utterances x %d s, best of 3 (%.2f s per pass)" % (

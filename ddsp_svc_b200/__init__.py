@@ -2,8 +2,10 @@
 yxlllc/DDSP-SVC, behind the reference's Sins / CombSub / CombSubSuperFast / SineGen forward()
 API.  See DESIGN.md for the path, its boundary and the kernels; include/b200ddsp.h for the C ABI.
 """
-from . import _lib, ops, synthetic  # noqa: F401
+from . import _lib, ops, sharding, synthetic  # noqa: F401
+from .dropin import build_model, load_model, patch_reference, unpatch_reference  # noqa: F401
 from .sinegen import SineGen  # noqa: F401
 from .vocoder import CombSub, CombSubSuperFast, FixedControls, Sins  # noqa: F401
 
-__all__ = ["Sins", "CombSub", "CombSubSuperFast", "SineGen", "FixedControls", "ops", "synthetic"]
+__all__ = ["Sins", "CombSub", "CombSubSuperFast", "SineGen", "FixedControls", "ops", "synthetic", "sharding",
+           "patch_reference", "unpatch_reference", "load_model", "build_model"]

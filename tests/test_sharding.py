@@ -1,0 +1,65 @@
+"""Host logic of the multi-GPU path, on CPU with the gloo backend and world_size 2 (and 3 for
+ragged shards): contiguous batch split, global utterance offsets, gather order."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ddsp_svc_b200 import sharding
+
+
+def test_shard_bounds_cover_the_batch():
+    for n in (1, 2, 7, 32, 256):
+        for w in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = sharding.shard_sizes(n, w)
+            assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_global, chunks, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = 64
+        s, e = sharding.shard_bounds(n_global, world, rank)
+        # each global utterance u is a waveform filled with u + t/1000: stands in for the synthesis,
+        # which depends only on the GLOBAL utterance index (utterance_offset = s)
+        rows = torch.arange(s, e, dtype=torch.float32)[:, None] + torch.arange(T, dtype=torch.float32)[None, :] / 1000
+        out = sharding.gather_waveform(rows, n_global, dst=0, chunks=chunks)
+        if rank == 0:
+            want = torch.arange(n_global, dtype=torch.float32)[:, None] + torch.arange(T, dtype=torch.float32)[None, :] / 1000
+            ret.put(bool(torch.equal(out, want)))
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_global,chunks", [(2, 8, 1), (2, 7, 1), (3, 8, 2), (2, 8, 4)])
+def test_gather_waveform_gloo(world, n_global, chunks):
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_global, chunks, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get() is True
