@@ -21,6 +21,10 @@
 //    envelope and written with 128-bit stores as soon as its 4th frame has been added, so the
 //    output is written exactly once and deterministically (no atomics, no workspace round trip).
 // The 3 extra frames per chunk are recomputed by the neighbouring CTAs (G = 29 -> 10 %).
+// The un-windowed source (comb, noise) of the current frame is kept in shared memory and shifted
+// by one hop per frame, so every source sample is evaluated once per CTA (not once per
+// overlapping frame); the frame's four control rows are prefetched into registers before the
+// forward FFT so their DRAM latency hides behind it.
 //
 // The reference's fp32 operation order is kept for the source (its in-frame phase is fp32 and the
 // sinc argument amplifies rounding by 1/s), the frame scan accumulates in fp64 like torch's CPU
@@ -31,7 +35,8 @@ namespace {
 
 constexpr int kN = 2048, kHalf = 1024, kThreads = 128;
 constexpr int kPadN = kN + kN / 16;  // padded complex buffer length
-constexpr int kRing = 4096;
+constexpr int kRingHops = 6;            // OLA ring: 6 hops of 512 (5 are live at any time)
+constexpr int kHop = 512;
 constexpr int kScanThreads = 256;
 
 __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
@@ -130,21 +135,35 @@ template <int R> struct Dft {
 
 // One Stockham pass of radix R over the padded buffer (in place: all reads, barrier, all writes).
 //   butterfly j: v[r] = buf[j + r N/R] * tw[r][j % Ns];  DFT_R;  buf[(j/Ns) Ns R + j%Ns + r Ns] = v[r]
-// tw: [R-1][Ns] table (row r-1), nullptr for the first pass (Ns = 1).
-template <int R, int NS>
+// Padded positions are affine in r for all three passes (padi(i) = i + i/16):
+//   reads : padi(j + r N/R)           = padi(j) + r (N/R + N/R/16)
+//   writes: NS = 1   -> 17 j + r ;  NS = 16 -> (j/16) 272 + j%16 + 17 r ;  NS = 256 -> padi(j) + 272 r
+// TW: 0 none (first pass), 1 full table [R-1][NS], 2 powers of tw[k] (= exp(-2 pi i k / (NS R)))
+template <int R, int NS, int TW>
 __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__ tw, int tid) {
     constexpr int NB = kN / R;               // butterflies
     constexpr int PER = NB / kThreads;       // per thread (1 for R=16, 2 for R=8)
+    constexpr int RS = NB + NB / 16;         // read stride in padded slots
     float2 v[PER][R];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int j = tid + u * kThreads;
         const int k = j % NS;
+        const float2* src = buf + padi(j);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float2 x = buf[padi(j + r * NB)];
-            if (NS > 1 && r > 0) x = cmul(x, tw[(r - 1) * NS + k]);
-            v[u][r] = x;
+        for (int r = 0; r < R; ++r) v[u][r] = src[r * RS];
+        if (TW == 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[u][r] = cmul(v[u][r], tw[(r - 1) * NS + k]);
+        } else if (TW == 2) {
+            const float2 w1 = tw[k];
+            const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+            v[u][1] = cmul(v[u][1], w1); v[u][2] = cmul(v[u][2], w2);
+            v[u][3] = cmul(v[u][3], w3); v[u][4] = cmul(v[u][4], w4);
+            if (R > 5) {
+                const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+                v[u][5] = cmul(v[u][5], w5); v[u][6] = cmul(v[u][6], w6); v[u][7] = cmul(v[u][7], w7);
+            }
         }
         Dft<R>::run(v[u]);
     }
@@ -152,18 +171,21 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int j = tid + u * kThreads;
-        const int k = j % NS;
-        const int base = (j / NS) * NS * R + k;
+        float2* dst;
+        int ws;
+        if (NS == 1) { dst = buf + 17 * j; ws = 1; }
+        else if (NS == 16) { dst = buf + (j >> 4) * 272 + (j & 15); ws = 17; }
+        else { dst = buf + padi(j); ws = 272; }
 #pragma unroll
-        for (int r = 0; r < R; ++r) buf[padi(base + r * NS)] = v[u][r];
+        for (int r = 0; r < R; ++r) dst[r * ws] = v[u][r];
     }
     __syncthreads();
 }
 
 __device__ __forceinline__ void fft2048(float2* buf, const float2* tw2, const float2* tw3, int tid) {
-    fft_pass<16, 1>(buf, nullptr, tid);
-    fft_pass<16, 16>(buf, tw2, tid);
-    fft_pass<8, 256>(buf, tw3, tid);
+    fft_pass<16, 1, 0>(buf, nullptr, tid);
+    fft_pass<16, 16, 1>(buf, tw2, tid);
+    fft_pass<8, 256, 2>(buf, tw3, tid);
 }
 
 struct SfParams {
@@ -178,21 +200,33 @@ struct SfParams {
     long long utt_off;
 };
 
-__device__ __forceinline__ float sinc_f32(float z) {   // torch.sinc in fp32
+// sinc(z) = sin(pi z)/(pi z).  |pi z| reaches ~1e3 rad, so the argument is reduced in turns
+// (exactly: z - 2 rint(z/2)) and the SFU evaluates sin(pi r); for |pi z| < 1 an even polynomial
+// avoids the SFU's absolute error being divided by a small number.
+__device__ __forceinline__ float sinc_f32(float z) {
     const float pz = __fmul_rn(B2D_PI_F, z);
-    return (z == 0.0f) ? 1.0f : __fdiv_rn(sinf(pz), pz);
+    const float p2 = pz * pz;
+    // 1 - x^2/6 + x^4/120 - x^6/5040 + x^8/362880 - x^10/39916800
+    float poly = fmaf(p2, -2.5052108e-8f, 2.7557319e-6f);
+    poly = fmaf(p2, poly, -1.9841270e-4f);
+    poly = fmaf(p2, poly, 8.3333333e-3f);
+    poly = fmaf(p2, poly, -1.6666667e-1f);
+    poly = fmaf(p2, poly, 1.0f);
+    const float r = fmaf(-2.0f, rintf(0.5f * z), z);          // z mod 2 in [-1, 1], exact
+    const float big = __fdividef(__sinf(B2D_PI_F * r), pz);
+    return (p2 < 1.0f) ? poly : big;
 }
 
 __device__ __forceinline__ float comb_at(const float4* __restrict__ fp, int P, float fP, int m) {
-    const int k = m / P, j = m - k * P;
+    const int k = m >> 9, j = m & (kHop - 1);            // P = 512 (checked on the host)
     const float4 q = __ldg(fp + k);                      // (s, ds, acc_prev)
     const float fj = (float)j, fj1 = (float)(j + 1);
     const float t1 = __fmul_rn(q.x, fj1);
     float t2 = __fmul_rn(__fmul_rn(__fmul_rn(0.5f, q.y), fj), fj1);
-    t2 = __fdiv_rn(t2, fP);
+    t2 = __fmul_rn(t2, 1.0f / 512.0f);                   // == t2 / P exactly (power of two)
     float rad = __fadd_rn(__fadd_rn(t1, t2), q.z);       // (:643,647)
     rad = __fsub_rn(rad, rintf(rad));                     // (:648)
-    const float sup = __fadd_rn(q.x, __fdiv_rn(__fmul_rn(q.y, fj), fP));   // (:644)
+    const float sup = __fadd_rn(q.x, __fmul_rn(__fmul_rn(q.y, fj), 1.0f / 512.0f));   // (:644)
     return sinc_f32(__fdiv_rn(rad, __fadd_rn(sup, 1e-5f)));                // (:649)
 }
 
@@ -210,14 +244,22 @@ __device__ __forceinline__ float4 normals4(unsigned long long seed, unsigned lon
     return make_float4(m1 * c1, m1 * s1, m2 * c2, m2 * s2);
 }
 
-__global__ void __launch_bounds__(kThreads) superfast_kernel(SfParams p) {
+// shared-memory footprint (bytes): 2 x 17408 (bufA, bufS) + 16384 (src) + 12288 (ring) + 4112 (win)
+// + 1920 (tw2) + 2048 (tw3) = 71568  -> 3 CTAs per SM
+constexpr int kWinLen = kHalf + 4;   // window stored for i in [0, 1024]; win[i] = win[2048 - i]
+constexpr size_t kSmemBytes = (size_t)2 * kPadN * sizeof(float2) + (size_t)kN * sizeof(float2) +
+                              (size_t)kRingHops * kHop * sizeof(float) + (size_t)kWinLen * sizeof(float) +
+                              (size_t)(15 * 16 + 256) * sizeof(float2);
+
+__global__ void __launch_bounds__(kThreads, 3) superfast_kernel(SfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);          // [kPadN] frame time/frequency data
     float2* bufS = bufA + kPadN;                                 // [kPadN] pair spectrum / pair output
-    float2* tw2 = bufS + kPadN;                                  // [15][16]
-    float2* tw3 = tw2 + 15 * 16;                                 // [7][256]
-    float* ring = reinterpret_cast<float*>(tw3 + 7 * 256);       // [kRing]
-    float* win = ring + kRing;                                   // [kN]
+    float2* src = bufS + kPadN;                                  // [kN]   un-windowed (comb, noise), ring-indexed
+    float2* tw2 = src + kN;                                      // [15][16]  exp(-2 pi i r k / 256)
+    float2* tw3 = tw2 + 15 * 16;                                 // [256]     exp(-2 pi i k / 2048)
+    float* ring = reinterpret_cast<float*>(tw3 + 256);           // [6][512]  overlap-add
+    float* winh = ring + kRingHops * kHop;                       // [1025]    periodic Hann, first half
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
@@ -230,21 +272,62 @@ __global__ void __launch_bounds__(kThreads) superfast_kernel(SfParams p) {
     const unsigned long long utt = (unsigned long long)(p.utt_off + b);
 
     // ---- one-time tables ----
-    for (int i = tid; i < kN; i += kThreads) win[i] = 0.5f - 0.5f * cospif((float)i * (2.0f / kN));
-    for (int i = tid; i < 15 * 16; i += kThreads) {              // pass 2: exp(-2 pi i r k / 256)
+    for (int i = tid; i <= kHalf; i += kThreads) winh[i] = 0.5f - 0.5f * cospif((float)i * (2.0f / kN));
+    for (int i = tid; i < 15 * 16; i += kThreads) {
         const int r = i / 16 + 1, k = i % 16;
-        float s, c; sincospif(-2.0f * (float)(r * k) / 256.0f, &s, &c);
-        tw2[i] = make_float2(c, s);
+        float sn, cs; sincospif(-2.0f * (float)(r * k) / 256.0f, &sn, &cs);
+        tw2[i] = make_float2(cs, sn);
     }
-    for (int i = tid; i < 7 * 256; i += kThreads) {              // pass 3: exp(-2 pi i r k / 2048)
-        const int r = i / 256 + 1, k = i % 256;
-        float s, c; sincospif(-2.0f * (float)(r * k) / 2048.0f, &s, &c);
-        tw3[i] = make_float2(c, s);
+    for (int i = tid; i < 256; i += kThreads) {
+        float sn, cs; sincospif(-2.0f * (float)i / 2048.0f, &sn, &cs);
+        tw3[i] = make_float2(cs, sn);
     }
-    for (int i = tid; i < kRing; i += kThreads) ring[i] = 0.f;
+    for (int i = tid; i < kRingHops * kHop; i += kThreads) ring[i] = 0.f;
     __syncthreads();
+    auto win_at = [&](int i) { return winh[i <= kHalf ? i : kN - i]; };
+
+    // source samples of absolute positions [mstart + i_lo, mstart + i_hi) -> src ring slots (i + off) & 2047
+    auto fill_src = [&](int mstart, int off, int i_lo, int i_hi) {
+#pragma unroll 1
+        for (int i0 = i_lo + (tid << 2); i0 < i_hi; i0 += kThreads << 2) {
+            const int m0 = mstart + i0;
+            float cv[4], nv[4];
+            if (m0 >= 0 && m0 + 3 < T) {
+                float4 nz;
+                if (noise_row) nz = __ldg(reinterpret_cast<const float4*>(noise_row + m0));   // m0 % 4 == 0
+                else nz = normals4(p.seed, utt, (uint32_t)(m0 >> 2));
+                nv[0] = nz.x; nv[1] = nz.y; nv[2] = nz.z; nv[3] = nz.w;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cv[e] = comb_at(fpar, P, fP, m0 + e);
+            } else {
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) {
+                    int m = m0 + e;
+                    bool valid = true;
+                    if (m < 0 || m >= T) {
+                        if (reflect) m = (m < 0) ? -m : 2 * (T - 1) - m;
+                        else valid = false;
+                    }
+                    cv[e] = 0.f; nv[e] = 0.f;
+                    if (valid) {
+                        cv[e] = comb_at(fpar, P, fP, m);
+                        if (noise_row) nv[e] = noise_row[m];
+                        else {
+                            const float4 g = normals4(p.seed, utt, (uint32_t)(m >> 2));
+                            const int l = m & 3;
+                            nv[e] = l == 0 ? g.x : l == 1 ? g.y : l == 2 ? g.z : g.w;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) src[(i0 + e + off) & (kN - 1)] = make_float2(cv[e], nv[e]);
+        }
+    };
 
     const int qs = max(h0 - 1, 0), qe = min(h1 + 1, nF);
+    int off = 0;            // src ring offset of the current frame's sample 0
+    bool primed = false;
 
     for (int qa = qs; qa <= qe; qa += 2) {
         const int qb = qa + 1;
@@ -253,79 +336,52 @@ __global__ void __launch_bounds__(kThreads) superfast_kernel(SfParams p) {
         for (int which = 0; which < 2; ++which) {
             if (which == 1 && !has_b) break;
             const int q = which ? qb : qa;
-            // ---- windowed complex frame: z[i] = win[i] * (comb[m] + j noise[m]), m = qP - 1024 + i ----
             const int mstart = q * P - kHalf;
-#pragma unroll 1
-            for (int it = 0; it < kN / 4 / kThreads; ++it) {
-                const int i0 = (tid + it * kThreads) << 2;
-                const int m0 = mstart + i0;
-                float cv[4], nv[4];
-                if (m0 >= 0 && m0 + 3 < T) {
-                    float4 nz;
-                    if (noise_row) {
-                        if ((m0 & 3) == 0) nz = __ldg(reinterpret_cast<const float4*>(noise_row + m0));
-                        else nz = make_float4(noise_row[m0], noise_row[m0 + 1], noise_row[m0 + 2], noise_row[m0 + 3]);
-                    } else if ((m0 & 3) == 0) {
-                        nz = normals4(p.seed, utt, (uint32_t)(m0 >> 2));
-                    } else {
-                        float t[4];
-                        for (int e = 0; e < 4; ++e) {
-                            const float4 g = normals4(p.seed, utt, (uint32_t)((m0 + e) >> 2));
-                            const int l = (m0 + e) & 3;
-                            t[e] = l == 0 ? g.x : l == 1 ? g.y : l == 2 ? g.z : g.w;
-                        }
-                        nz = make_float4(t[0], t[1], t[2], t[3]);
-                    }
-                    nv[0] = nz.x; nv[1] = nz.y; nv[2] = nz.z; nv[3] = nz.w;
+            // ---- source: first frame of the CTA evaluates 2048 samples, later frames only the new hop ----
+            if (!primed) { fill_src(mstart, off, 0, kN); primed = true; }
+            else { off = (off + kHop) & (kN - 1); fill_src(mstart, off, kN - kHop, kN); }
+            __syncthreads();
+            // ---- windowed complex frame z[i] = win[i] * (comb + j noise) ----
+#pragma unroll 4
+            for (int i = tid; i < kN; i += kThreads) {
+                const float2 v = src[(i + off) & (kN - 1)];
+                const float w = win_at(i);
+                bufA[padi(i)] = make_float2(w * v.x, w * v.y);
+            }
+            // ---- prefetch this frame's controls (bins tid + 128 it, and bin 1024 on thread 0) ----
+            const int qc = min(q, nF - 1);
+            const size_t crow = ((size_t)b * nF + qc) * p.ctrl_stride;
+            float chm[9], chp[9], cnm[9], cnp[9];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) cv[e] = comb_at(fpar, P, fP, m0 + e);
-                } else {
-#pragma unroll 1
-                    for (int e = 0; e < 4; ++e) {
-                        int m = m0 + e;
-                        bool valid = true;
-                        if (m < 0 || m >= T) {
-                            if (reflect) m = (m < 0) ? -m : 2 * (T - 1) - m;
-                            else valid = false;
-                        }
-                        if (valid) {
-                            cv[e] = comb_at(fpar, P, fP, m);
-                            if (noise_row) nv[e] = noise_row[m];
-                            else {
-                                const float4 g = normals4(p.seed, utt, (uint32_t)(m >> 2));
-                                const int l = m & 3;
-                                nv[e] = l == 0 ? g.x : l == 1 ? g.y : l == 2 ? g.z : g.w;
-                            }
-                        } else { cv[e] = 0.f; nv[e] = 0.f; }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float w = win[i0 + e];
-                    bufA[padi(i0 + e)] = make_float2(w * cv[e], w * nv[e]);
-                }
+            for (int it = 0; it < 8; ++it) {
+                const size_t o = crow + tid + it * kThreads;
+                chm[it] = __ldg(p.c_hm + o); chp[it] = __ldg(p.c_hp + o);
+                cnm[it] = __ldg(p.c_nm + o); cnp[it] = __ldg(p.c_np + o);
+            }
+            chm[8] = chp[8] = cnm[8] = cnp[8] = 0.f;
+            if (tid == 0) {
+                chm[8] = __ldg(p.c_hm + crow + kHalf); chp[8] = __ldg(p.c_hp + crow + kHalf);
+                cnm[8] = __ldg(p.c_nm + crow + kHalf); cnp[8] = __ldg(p.c_np + crow + kHalf);
             }
             __syncthreads();
             fft2048(bufA, tw2, tw3, tid);
             // ---- split comb/noise spectra, apply the filters, accumulate the pair spectrum ----
-            const int qc = min(q, nF - 1);
-            const size_t crow = ((size_t)b * nF + qc) * p.ctrl_stride;
-#pragma unroll 1
-            for (int bin = tid; bin <= kHalf; bin += kThreads) {
+#pragma unroll
+            for (int it = 0; it < 9; ++it) {
+                const int bin = (it < 8) ? tid + it * kThreads : kHalf;
+                if (it == 8 && tid != 0) break;
                 const float2 za = bufA[padi(bin)];
                 float2 zb = bufA[padi((kN - bin) & (kN - 1))];
                 zb.y = -zb.y;                                                   // conj
                 const float2 X = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y + zb.y));
                 const float2 d = csub(za, zb);
                 const float2 Nz = make_float2(0.5f * d.y, -0.5f * d.x);
-                const float hm = __ldg(p.c_hm + crow + bin), hp = __ldg(p.c_hp + crow + bin);
-                const float nm = __ldg(p.c_nm + crow + bin), np = __ldg(p.c_np + crow + bin);
                 float sh, ch, sn, cn;
-                sincosf(__fmul_rn(B2D_PI_F, hp), &sh, &ch);
-                sincosf(__fmul_rn(B2D_PI_F, np), &sn, &cn);
-                const float eh = expf(hm), en = expf(nm);
+                __sincosf(B2D_PI_F * chp[it], &sh, &ch);
+                __sincosf(B2D_PI_F * cnp[it], &sn, &cn);
+                const float eh = __expf(chm[it]), en = __expf(cnm[it]) * 0.0078125f;   // /128 (:668)
                 const float2 Hs = make_float2(eh * ch, eh * sh);                 // exp(m + j pi p)  (:666)
-                const float2 Hn = make_float2(en * cn * 0.0078125f, en * sn * 0.0078125f);   // /128 (:668)
+                const float2 Hn = make_float2(en * cn, en * sn);
                 float2 Y = cadd(cmul(X, Hs), cmul(Nz, Hn));                      // (:699)
                 if (bin == 0 || bin == kHalf) Y.y = 0.f;                         // irfft ignores Im of DC / Nyquist
                 // pair spectrum S = Ya + j Yb with Hermitian extension, stored re/im SWAPPED so that a
@@ -335,13 +391,12 @@ __global__ void __launch_bounds__(kThreads) superfast_kernel(SfParams p) {
                     bufS[padi(bin)] = make_float2(Y.y, Y.x);
                     if (bin != 0 && bin != kHalf) bufS[padi(mir)] = make_float2(-Y.y, Y.x);
                 } else {
-                    // j*Y = (-Y.im, Y.re) ; j*conj(Y) = (Y.im, Y.re)   (swapped when stored)
                     float2 s0 = bufS[padi(bin)];
-                    s0.x += Y.x; s0.y += -Y.y;
+                    s0.x += Y.x; s0.y -= Y.y;                                    // += j*Y       (swapped)
                     bufS[padi(bin)] = s0;
                     if (bin != 0 && bin != kHalf) {
                         float2 s1 = bufS[padi(mir)];
-                        s1.x += Y.x; s1.y += Y.y;
+                        s1.x += Y.x; s1.y += Y.y;                                // += j*conj(Y) (swapped)
                         bufS[padi(mir)] = s1;
                     }
                 }
@@ -351,13 +406,16 @@ __global__ void __launch_bounds__(kThreads) superfast_kernel(SfParams p) {
         // ---- inverse transform of the pair, windowed overlap-add into the ring ----
         fft2048(bufS, tw2, tw3, tid);
         const float inv_n = 1.0f / (float)kN;
-#pragma unroll 1
+        int hslot[5];       // ring slot (x512) of hops qa-2 .. qa+2
+#pragma unroll
+        for (int t = 0; t < 5; ++t) hslot[t] = ((qa - 2 + t + 6 * 1024) % kRingHops) * kHop;
+#pragma unroll 4
         for (int i = tid; i < kN; i += kThreads) {
-            const float2 s = bufS[padi(i)];        // swapped: (im, re)
-            const float w = win[i] * inv_n;
-            const int na = qa * P - kHalf + i;
-            ring[(na + kRing) & (kRing - 1)] += s.y * w;
-            if (has_b) ring[(na + P + kRing) & (kRing - 1)] += s.x * w;
+            const float2 sv = bufS[padi(i)];       // swapped: (im, re)
+            const float w = win_at(i) * inv_n;
+            const int hi = i >> 9, lo = i & (kHop - 1);
+            ring[hslot[hi] + lo] += sv.y * w;
+            if (has_b) ring[hslot[hi + 1] + lo] += sv.x * w;
         }
         __syncthreads();
         // ---- hops whose 4 frames are in: qa-2, qa-1; at the last pair everything up to h1-1 ----
@@ -365,26 +423,24 @@ __global__ void __launch_bounds__(kThreads) superfast_kernel(SfParams p) {
         const int h_hi = (last >= qe) ? max(h1 - 1, qa - 1) : qa - 1;
         for (int h = qa - 2; h <= h_hi; ++h) {
             const bool owned = h >= h0 && h < h1;
-#pragma unroll 1
-            for (int i4 = tid << 2; i4 < P; i4 += kThreads << 2) {
+            float* rrow = ring + ((h + 6 * 1024) % kRingHops) * kHop;
+            const int i4 = tid << 2;               // 128 threads x 4 samples = one hop
+            const float4 acc = *reinterpret_cast<const float4*>(rrow + i4);
+            *reinterpret_cast<float4*>(rrow + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (owned) {
                 const int n = h * P + i4;
-                const int ri = (n + kRing) & (kRing - 1);
-                const float4 acc = *reinterpret_cast<const float4*>(ring + ri);
-                *reinterpret_cast<float4*>(ring + ri) = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (owned) {
-                    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+                float v[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float env = 0.f;     // OLA(win^2) over the frames that exist
+                for (int e = 0; e < 4; ++e) {
+                    float env = 0.f;     // OLA(win^2) over the frames that exist
 #pragma unroll
-                        for (int d = -1; d <= 2; ++d) {
-                            const int qq = h + d;
-                            if (qq >= 0 && qq <= nF) { const float w = win[n + e - qq * P + kHalf]; env = fmaf(w, w, env); }
-                        }
-                        v[e] = __fdiv_rn(v[e], env);
+                    for (int d = -1; d <= 2; ++d) {
+                        const int qq = h + d;
+                        if (qq >= 0 && qq <= nF) { const float w = win_at(i4 + e - d * kHop + kHalf); env = fmaf(w, w, env); }
                     }
-                    b2d::st_global_v4(p.out + (size_t)b * T + n, make_float4(v[0], v[1], v[2], v[3]));
+                    v[e] = __fdiv_rn(v[e], env);
                 }
+                b2d::st_global_v4(p.out + (size_t)b * T + n, make_float4(v[0], v[1], v[2], v[3]));
             }
         }
         __syncthreads();
@@ -433,8 +489,7 @@ extern "C" int b2d_superfast_synth(const void* workspace, const float* c_harmoni
     while (G > 5 && (long long)B * ((n_frames + G - 1) / G) < 4 * 148) G -= 4;
     p.G = G;
     p.seed = seed; p.utt_off = utterance_offset;
-    const size_t smem = (size_t)2 * kPadN * sizeof(float2) + (15 * 16 + 7 * 256) * sizeof(float2) +
-                        (kRing + kN) * sizeof(float);
+    const size_t smem = kSmemBytes;
     cudaError_t e = cudaFuncSetAttribute(superfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return b2d::fail((int)e, "superfast_synth: smem attr: %s", cudaGetErrorString(e));
     cudaFuncSetAttribute(superfast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
