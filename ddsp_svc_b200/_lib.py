@@ -37,6 +37,7 @@ SIGNATURES = {
     "b2d_ltv_fir": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_int, c_f32p,
                                    c_f32p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, c_stream]),
+    "b2d_set_fir_impl": (ctypes.c_int, [ctypes.c_int]),
     "b2d_ltv_fir_generic": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, c_f32p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, c_stream]),
     "b2d_sins_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),

@@ -274,6 +274,16 @@ __global__ void ltv_fir_generic_kernel(const float* __restrict__ x, const float*
 
 namespace b2d {
 
+int ltv_fir_tc_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
+                      int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
+                      int nF, int P, cudaStream_t st);
+
+// 0 = auto, 1 = CUDA-core kernel, 2 = tensor-core kernel (block size 512 only).
+// auto = CUDA cores: measured on B200 (B=32 x 10 s, two 510-tap filters) the tcgen05 kernel takes
+// 4.20 ms against 1.26 ms -- with N = 8 columns every MMA re-reads its 4 KB Hankel operand from
+// shared memory for 16 kflop, so it is operand-bandwidth bound (~56 cycles per 128x8x8 MMA).
+static int g_fir_impl = 0;
+
 // internal entry (also used by the CombSub driver): mix = y1 (+ y2) (+ addend)
 int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
                    int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
@@ -284,6 +294,18 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
         return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: tiled kernel needs block size multiple of 256 (got %d); use b2d_ltv_fir_generic", P);
     if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: batch %d > 65535", B);
     const int njobs = ir2 ? 2 : 1;
+    {
+        const int impl = g_fir_impl;
+        const bool tc_ok = (P == 512) && !(njobs == 2 && (taps1 != taps2 || addend));
+        if (impl == 2 && !tc_ok) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: tensor-core kernel needs block size 512");
+        if (impl == 2) {
+            const float* ptrs0[] = {x1, x2, y1, y2, addend, mix};
+            for (const float* q : ptrs0)
+                if (q && !aligned16(q)) return fail(B2D_ERR_ALIGN, "ltv_fir: signal pointers must be 16-byte aligned");
+            if (taps1 <= 0 || (taps1 & 1) || (njobs == 2 && (taps2 <= 0 || (taps2 & 1)))) return fail(B2D_ERR_SHAPE, "ltv_fir: bad tap count");
+            return ltv_fir_tc_launch(x1, ir1, taps1, y1, x2, ir2, taps2, y2, addend, mix, seed, utt_off, B, nF, P, st);
+        }
+    }
     if (njobs == 2) {
         if (taps2 <= 0 || (taps2 & 1)) return fail(B2D_ERR_SHAPE, "ltv_fir: bad taps2");
         // each job's output tile starts at fP - (L/2+1): only equal tap counts share a tile
@@ -323,6 +345,12 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
 }
 
 }  // namespace b2d
+
+extern "C" int b2d_set_fir_impl(int impl) {
+    if (impl < 0 || impl > 2) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
+    b2d::g_fir_impl = impl;
+    return 0;
+}
 
 extern "C" int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1, const float* x2,
                            const float* ir2, int taps2, float* y2, float* mix, uint64_t seed,

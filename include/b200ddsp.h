@@ -109,6 +109,12 @@ int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1,
                 float* mix, uint64_t seed, int64_t utterance_offset,
                 int B, int n_frames, int block, void* stream);
 
+/* Two implementations of the tiled kernel exist: CUDA cores (default; block size multiple of
+ * 256) and tcgen05 tensor cores (3xTF32, block size 512; correct but operand-bandwidth bound and
+ * ~3x slower on B200).  0 = automatic (CUDA cores), 1 = CUDA cores, 2 = tensor
+ * cores.  Process-wide test/diagnostic knob. */
+int b2d_set_fir_impl(int impl);
+
 /* Same result by the plain one-thread-per-sample formula (any block size / tap count);
  * used as the fallback for configurations the tiled kernel does not cover and as an
  * on-device cross-check. One job only. */
