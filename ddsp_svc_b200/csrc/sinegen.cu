@@ -62,7 +62,10 @@ struct SgParams {
     const float* noise_in;  // [B, T, dim] or nullptr
     float* out;             // [B, T, dim]
     int nF, upp, dim;
-    float sr, sine_amp, noise_std, thr;
+    int upp_shift;          // log2(upp) if upp is a power of two, else -1
+    float sr, sine_amp;
+    float namp_voiced, namp_unvoiced;   // uv*noise_std + (1-uv)*sine_amp/3 for uv = 1 / 0 (fp32, reference op order)
+    float thr;
     unsigned long long seed;
     long long utt_off;
 };
@@ -75,13 +78,16 @@ __device__ __forceinline__ float sin_reduced(float arg) {
     return __sinf(r);
 }
 
+// DIM > 0: compile-time number of harmonics (fully unrolled, no predication); DIM == 0: runtime p.dim <= 16
+template <int DIM>
 __global__ void __launch_bounds__(kTile) sinegen_kernel(SgParams p) {
     extern __shared__ __align__(16) float tile[];  // [kTile * dim]
+    constexpr int MAXD = DIM > 0 ? DIM : kMaxDim;
+    const int dim = DIM > 0 ? DIM : p.dim;
     const int b = blockIdx.y;
     const int T = p.nF * p.upp;
     const int t0 = blockIdx.x * kTile;
     const int nt = min(kTile, T - t0);
-    const int dim = p.dim;
     const int tid = threadIdx.x;
     const size_t base = ((size_t)b * T + t0) * dim;
     const int nflat = nt * dim;
@@ -99,32 +105,36 @@ __global__ void __launch_bounds__(kTile) sinegen_kernel(SgParams p) {
 
     if (tid < nt) {
         const int t = t0 + tid;
-        const int k = t / p.upp, j = t - k * p.upp;
+        int k, j;
+        if (p.upp_shift >= 0) { k = t >> p.upp_shift; j = t & (p.upp - 1); }
+        else { k = t / p.upp; j = t - k * p.upp; }
         const float f = p.f0[(size_t)b * p.nF + k];
         const float s = __fdiv_rn(f, p.sr);                                             // f0 / sr
         const float rad = __fadd_rn(__fmul_rn(s, (float)(j + 1)), p.acc_prev[(size_t)b * p.nF + k]);  // (:138,141)
-        const float uv = f > p.thr ? 1.0f : 0.0f;
-        const float namp = __fadd_rn(__fmul_rn(uv, p.noise_std), __fdiv_rn(__fmul_rn(1.0f - uv, p.sine_amp), 3.0f));
+        const bool voiced = f > p.thr;
+        const float namp = voiced ? p.namp_voiced : p.namp_unvoiced;                    // (:162)
+        const float samp_uv = voiced ? p.sine_amp : 0.0f;   // (sin*sine_amp)*uv == sin*(sine_amp*uv) for uv in {0,1}
         float* row = tile + tid * dim;
-        float eps[kMaxDim];
+        float eps[MAXD + 3];
         if (p.noise_in) {
 #pragma unroll
-            for (int h = 0; h < kMaxDim; ++h) if (h < dim) eps[h] = row[h];
+            for (int h = 0; h < MAXD; ++h) if (h < dim) eps[h] = row[h];
         } else {
             // 4 normals per Philox call; counter = (sample index, call index), key = seed,
             // stream = utterance.  ceil(dim/4) calls per sample (3 for dim = 9; 3 normals unused).
             const unsigned long long utt = (unsigned long long)(p.utt_off + b);
 #pragma unroll
-            for (int c = 0; c < kMaxDim / 4; ++c) {
+            for (int c = 0; c < (MAXD + 3) / 4; ++c) {
                 if (4 * c < dim) {
                     uint4 r = b2d::philox4x32_10(make_uint4((uint32_t)t, 0x51e6e000u + c, (uint32_t)utt, (uint32_t)(utt >> 32)),
                                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                    // Box-Muller: u1,u3 in (0,1], u2,u4 in [0,1)
+                    // Box-Muller: u1,u3 in (0,1], u2,u4 in [0,1);  sqrt(a) = a * rsqrt(a), a > 0
                     const float u1 = ((float)(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
                     const float u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);
                     const float u3 = ((float)(r.z >> 8) + 1.0f) * (1.0f / 16777216.0f);
                     const float u4 = (float)(r.w >> 8) * (1.0f / 16777216.0f);
-                    const float m1 = sqrtf(-2.0f * __logf(u1)), m2 = sqrtf(-2.0f * __logf(u3));
+                    const float a1 = fmaxf(-2.0f * __logf(u1), 1e-30f), a3 = fmaxf(-2.0f * __logf(u3), 1e-30f);
+                    const float m1 = a1 * rsqrtf(a1), m2 = a3 * rsqrtf(a3);
                     float s1, c1, s2, c2;
                     __sincosf(B2D_TWO_PI_F * u2, &s1, &c1);
                     __sincosf(B2D_TWO_PI_F * u4, &s2, &c2);
@@ -134,12 +144,11 @@ __global__ void __launch_bounds__(kTile) sinegen_kernel(SgParams p) {
             }
         }
 #pragma unroll
-        for (int h = 0; h < kMaxDim; ++h) {
+        for (int h = 0; h < MAXD; ++h) {
             if (h < dim) {
-                const float theta = __fadd_rn(__fmul_rn(rad, (float)(h + 1)), p.rand_ini[h]);   // (:143,146)
-                const float sn = sin_reduced(__fmul_rn(B2D_TWO_PI_F, theta));                    // (:147)
-                const float sine = __fmul_rn(sn, p.sine_amp);                                    // (:159)
-                row[h] = __fadd_rn(__fmul_rn(sine, uv), __fmul_rn(namp, eps[h]));               // (:163-164)
+                const float theta = __fadd_rn(__fmul_rn(rad, (float)(h + 1)), __ldg(p.rand_ini + h));   // (:143,146)
+                const float sn = sin_reduced(__fmul_rn(B2D_TWO_PI_F, theta));                             // (:147)
+                row[h] = __fadd_rn(__fmul_rn(sn, samp_uv), __fmul_rn(namp, eps[h]));                      // (:159,163-164)
             }
         }
     }
@@ -172,9 +181,18 @@ extern "C" int b2d_sinegen(const float* f0, const float* rand_ini, const float* 
     SgParams p;
     p.f0 = f0; p.acc_prev = acc_workspace; p.rand_ini = rand_ini; p.noise_in = noise_in; p.out = out;
     p.nF = n_frames; p.upp = upp; p.dim = dim;
-    p.sr = (float)sampling_rate; p.sine_amp = sine_amp; p.noise_std = noise_std; p.thr = voiced_threshold;
+    p.sr = (float)sampling_rate; p.sine_amp = sine_amp; p.thr = voiced_threshold;
+    p.upp_shift = -1;
+    for (int sft = 0; sft < 30; ++sft) if ((1 << sft) == upp) p.upp_shift = sft;
+    // noise_amp = uv*noise_std + (1-uv)*sine_amp/3 in fp32 with the reference's operation order (:162)
+    p.namp_voiced = (1.0f * noise_std) + ((0.0f * sine_amp) / 3.0f);
+    p.namp_unvoiced = (0.0f * noise_std) + ((1.0f * sine_amp) / 3.0f);
     p.seed = seed; p.utt_off = utterance_offset;
     const long long T = (long long)n_frames * upp;
-    sinegen_kernel<<<dim3((unsigned)((T + kTile - 1) / kTile), B), kTile, kTile * dim * sizeof(float), st>>>(p);
+    const dim3 grid((unsigned)((T + kTile - 1) / kTile), B);
+    const size_t smem = kTile * dim * sizeof(float);
+    if (dim == 9) sinegen_kernel<9><<<grid, kTile, smem, st>>>(p);
+    else if (dim == 1) sinegen_kernel<1><<<grid, kTile, smem, st>>>(p);
+    else sinegen_kernel<0><<<grid, kTile, smem, st>>>(p);
     return b2d::check_launch("sinegen");
 }
