@@ -266,6 +266,23 @@ class Runner:
             return self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B)
         return self.model(None, f0, None, utterance_offset=self.rank * self.B)[0]
 
+    # rows [lo, hi) of the local batch (for the chunked synth+gather pipeline) -> [hi-lo, row_len]
+    @property
+    def row_len(self):
+        return self.T * (self.w["dim"] if self.w["kind"] == "sinegen" else 1)
+
+    def step_rows(self, lo, hi):
+        f0 = self.f0_d[lo:hi]
+        if self.w["kind"] == "sinegen":
+            out = self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B + lo)
+            return out.reshape(hi - lo, -1)
+        full = self.fixed.ctrls
+        self.fixed.ctrls = self.syn.split_views(self.dense_d[lo:hi], self.sm)
+        try:
+            return self.model(None, f0, None, utterance_offset=self.rank * self.B + lo)[0]
+        finally:
+            self.fixed.ctrls = full
+
     # the same through HOST buffers: pinned inputs -> H2D -> public module API -> D2H of the result
     def step_e2e(self):
         f0_x = self.f0_h.to(self.dev, non_blocking=True)
@@ -328,6 +345,8 @@ def main():
     ap.add_argument("--workload", default="sins", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the waveform")
+    ap.add_argument("--gather-chunks", type=int, default=4,
+                    help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -355,11 +374,17 @@ def main():
     do_gather = world > 1 and not args.no_gather
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    n_chunks = args.gather_chunks
+
     def step():
-        sig = run.step()
-        if do_gather:
+        if not do_gather:
+            return run.step()
+        if n_chunks <= 1:
+            sig = run.step()
             sharding.gather_waveform(sig.reshape(B, -1), world * B, dst=0)
-        return sig
+            return sig
+        # chunked: the NCCL transfer of finished utterances overlaps the synthesis of the rest
+        return sharding.synthesize_and_gather(run.step_rows, B, world * B, run.row_len, dev, dst=0, chunks=n_chunks)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -437,7 +462,8 @@ def main():
                        "samples_per_utterance": T, "noise": "in-kernel Philox4x32-10",
                        "outputs": "signal+harmonic+noise" if w["kind"] in ("sins", "combsub") else "signal",
                        "parallelism": "batch-sharded x%d%s" % (
-                           world, ", NCCL gather of the waveform to rank 0 inside the step" if do_gather else ""),
+                           world, (", NCCL gather of the waveform to rank 0 inside the step (%d chunks, overlapped with synthesis)"
+                                   % n_chunks) if do_gather else ""),
                        "l2": "flushed between steps (256 MiB memset, untimed); per-step CUDA events summed",
                        "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -30,6 +30,7 @@ SIGNATURES = {
                                       ctypes.c_int, c_f64p, c_f32p, c_stream]),
     "b2d_sins_bank": (ctypes.c_int, [c_f32p, c_f64p, c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_f32p, c_stream]),
+    "b2d_set_ir_impl": (ctypes.c_int, [ctypes.c_int]),
     "b2d_dft_tables_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "b2d_dft_tables": (ctypes.c_int, [ctypes.c_int, c_f32p, c_stream]),
     "b2d_ir_build": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, c_f32p, c_f32p, ctypes.c_int,

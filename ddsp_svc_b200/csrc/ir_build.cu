@@ -222,16 +222,42 @@ int launch(const IrParams& p, cudaStream_t st) {
 
 }  // namespace
 
+namespace b2d {
+// tensor-core path (ir_build_tc.cu)
+int dft_image_launch(int M, float* img, cudaStream_t st);
+bool ir_tc_supported(int mode, int M);
+int ir_build_tc_launch(const float* c, int64_t ctrl_stride, int mode, const float* f0, const float* image, int B,
+                       int nF, int M, double sr, float* ir, cudaStream_t st);
+size_t tc_image_floats_host(int M);
+// 0 = auto (tensor cores when supported), 1 = CUDA cores, 2 = tensor cores
+static int g_ir_impl = 0;
+static inline size_t cc_table_bytes(int n_mag) {
+    const size_t b = (size_t)2 * (n_even(n_mag) + n_odd(n_mag)) * n_cols(n_mag) * sizeof(float);
+    return (b + 255) / 256 * 256;
+}
+}  // namespace b2d
+
+// buffer layout: [CUDA-core tables, padded to 256 B][tensor-core operand image]
 extern "C" size_t b2d_dft_tables_bytes(int n_mag) {
     if (n_mag < 2) return 0;
-    return (size_t)2 * (n_even(n_mag) + n_odd(n_mag)) * n_cols(n_mag) * sizeof(float);
+    return b2d::cc_table_bytes(n_mag) + b2d::tc_image_floats_host(n_mag) * sizeof(float);
+}
+
+extern "C" int b2d_set_ir_impl(int impl) {
+    if (impl < 0 || impl > 2) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_ir_impl: %d", impl);
+    b2d::g_ir_impl = impl;
+    return 0;
 }
 
 extern "C" int b2d_dft_tables(int n_mag, float* dft_tables, void* stream) {
     if (!dft_tables) return b2d::fail(B2D_ERR_NULL, "dft_tables: null pointer");
     if (n_mag < 2 || n_mag > 4097) return b2d::fail(B2D_ERR_SHAPE, "dft_tables: n_mag=%d out of range", n_mag);
+    if ((reinterpret_cast<uintptr_t>(dft_tables) & 255u) != 0) return b2d::fail(B2D_ERR_ALIGN, "dft_tables: buffer must be 256-byte aligned");
     dft_tables_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(n_mag, dft_tables);
-    return b2d::check_launch("dft_tables");
+    int rc = b2d::check_launch("dft_tables");
+    if (rc) return rc;
+    float* img = reinterpret_cast<float*>(reinterpret_cast<char*>(dft_tables) + b2d::cc_table_bytes(n_mag));
+    return b2d::dft_image_launch(n_mag, img, (cudaStream_t)stream);
 }
 
 extern "C" int b2d_ir_build(const float* c, int64_t ctrl_stride, int mode, const float* f0_frames,
@@ -249,6 +275,18 @@ extern "C" int b2d_ir_build(const float* c, int64_t ctrl_stride, int mode, const
     p.hw_num = 1.5f * (float)sampling_rate;
     p.ir = ir;
     cudaStream_t st = (cudaStream_t)stream;
+    if (mode != B2D_IR_ALLPASS && mode != B2D_IR_MAG_HANN && mode != B2D_IR_MAG_DYNAMIC)
+        return b2d::fail(B2D_ERR_UNSUPPORTED, "ir_build: unknown mode %d", mode);
+    {
+        const int impl = b2d::g_ir_impl;
+        const bool ok = b2d::ir_tc_supported(mode, n_mag);
+        if (impl == 2 && !ok) return b2d::fail(B2D_ERR_UNSUPPORTED, "ir_build: tensor-core path does not support n_mag=%d in mode %d", n_mag, mode);
+        if ((impl == 0 || impl == 2) && ok) {
+            if ((reinterpret_cast<uintptr_t>(dft_tables) & 255u) != 0) return b2d::fail(B2D_ERR_ALIGN, "ir_build: dft_tables must be 256-byte aligned");
+            const float* img = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dft_tables) + b2d::cc_table_bytes(n_mag));
+            return b2d::ir_build_tc_launch(c, ctrl_stride, mode, f0_frames, img, B, n_frames, n_mag, sampling_rate, ir, st);
+        }
+    }
     switch (mode) {
         case B2D_IR_ALLPASS: return launch<B2D_IR_ALLPASS>(p, st);
         case B2D_IR_MAG_HANN: return launch<B2D_IR_MAG_HANN>(p, st);

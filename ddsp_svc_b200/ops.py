@@ -23,6 +23,11 @@ def set_fir_impl(impl):
     _lib.check(_lib.lib().b2d_set_fir_impl({"auto": 0, "cuda": 1, "tc": 2}[impl]), "b2d_set_fir_impl")
 
 
+def set_ir_impl(impl):
+    """'auto' (tcgen05 when supported), 'cuda' (CUDA-core kernel) or 'tc' (tcgen05 3xTF32 kernel)."""
+    _lib.check(_lib.lib().b2d_set_ir_impl({"auto": 0, "cuda": 1, "tc": 2}[impl]), "b2d_set_ir_impl")
+
+
 def launches():
     return _launches
 
@@ -79,7 +84,7 @@ def dft_tables(n_mag, device):
                 raise ValueError("n_mag=%d out of range" % n_mag)
             t = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
             _lib.check(L.b2d_dft_tables(int(n_mag), t.data_ptr(), _stream()), "b2d_dft_tables")
-            _count(1)
+            _count(2)
             _tables[key] = t
     return t
 

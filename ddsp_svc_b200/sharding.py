@@ -64,3 +64,70 @@ def gather_waveform(local, n_global, dst=0, group=None, chunks=1):
 def _chunk_bounds(n, chunks):
     chunks = max(1, min(chunks, n)) if n > 0 else 1
     return [shard_bounds(n, chunks, c) for c in range(chunks) if shard_bounds(n, chunks, c)[1] > shard_bounds(n, chunks, c)[0]]
+
+
+def synthesize_and_gather(synth_chunk, n_local, n_global, n_samples, device, dst=0, group=None, chunks=4,
+                          dtype=torch.float32):
+    """Chunked synthesis with the gather of finished chunks overlapped on a side stream.
+
+    ``synth_chunk(lo, hi)`` synthesizes local rows [lo, hi) and returns a [hi-lo, n_samples] tensor
+    on the current stream.  While chunk c+1 is being synthesized, chunk c travels to rank ``dst``
+    (point-to-point over NCCL / NVLink).  Requires equal shard sizes.  Returns the gathered
+    [n_global, n_samples] tensor on ``dst`` (None elsewhere); the current stream waits for the
+    transfers before returning.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if n_local * world != n_global:
+        raise ValueError("synthesize_and_gather needs equal shards (%d x %d != %d)" % (n_local, world, n_global))
+    cuda = torch.device(device).type == "cuda"
+    out = torch.empty(n_global, n_samples, dtype=dtype, device=device) if rank == dst else None
+    bounds = _chunk_bounds(n_local, chunks)
+    main = torch.cuda.current_stream(device) if cuda else None
+    comm = _comm_stream(device) if cuda else None
+    keep, works = [], []
+    for lo, hi in bounds:
+        part = synth_chunk(lo, hi)
+        if part.shape != (hi - lo, n_samples):
+            raise ValueError("synth_chunk returned %s, expected %s" % (tuple(part.shape), (hi - lo, n_samples)))
+        keep.append(part)
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            comm.wait_event(ev)
+        ctx = torch.cuda.stream(comm) if cuda else _null_ctx()
+        with ctx:
+            if rank == dst:
+                out[dst * n_local + lo:dst * n_local + hi].copy_(part, non_blocking=True)
+                ops = [dist.P2POp(dist.irecv, out[r * n_local + lo:r * n_local + hi], r, group)
+                       for r in range(world) if r != dst]
+            else:
+                ops = [dist.P2POp(dist.isend, part, dst, group)]
+            if ops:
+                works.extend(dist.batch_isend_irecv(ops))
+    ctx = torch.cuda.stream(comm) if cuda else _null_ctx()
+    with ctx:
+        for w in works:
+            w.wait()
+    if cuda:
+        main.wait_stream(comm)
+    del keep
+    return out
+
+
+_comm_streams = {}
+
+
+def _comm_stream(device):
+    key = torch.device(device).index
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=device)
+    return _comm_streams[key]
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -84,6 +84,10 @@ int b2d_sins_bank(const float* f0_frames, const double* frame_phase, const float
  * b2d_dft_tables() (constant cos/sin matrices of the L-point inverse real DFT).
  * f0_frames is only read in mode B2D_IR_MAG_DYNAMIC (window half-width 1.5*sr/(f0+1e-3)).
  */
+/* Two implementations: tcgen05 tensor cores (3xTF32; default when the accumulators fit TMEM)
+ * and CUDA cores.  b2d_set_ir_impl: 0 = automatic, 1 = CUDA cores, 2 = tensor cores (test knob).
+ * The table buffer (256-byte aligned) holds the constant matrices for both. */
+int    b2d_set_ir_impl(int impl);
 size_t b2d_dft_tables_bytes(int n_mag);
 int    b2d_dft_tables(int n_mag, float* dft_tables, void* stream);
 int    b2d_ir_build(const float* c, int64_t ctrl_stride, int mode, const float* f0_frames,

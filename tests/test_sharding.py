@@ -63,3 +63,41 @@ def test_gather_waveform_gloo(world, n_global, chunks):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get() is True
+
+
+def _worker_pipeline(rank, world, port, n_local, chunks, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = 32
+        calls = []
+
+        def synth(lo, hi):
+            calls.append((lo, hi))
+            u = torch.arange(rank * n_local + lo, rank * n_local + hi, dtype=torch.float32)
+            return u[:, None] * 10 + torch.arange(T, dtype=torch.float32)[None, :] / 100
+
+        out = sharding.synthesize_and_gather(synth, n_local, n_local * world, T, "cpu", dst=0, chunks=chunks)
+        ok = calls == sharding._chunk_bounds(n_local, chunks)
+        if rank == 0:
+            want = torch.arange(n_local * world, dtype=torch.float32)[:, None] * 10 + torch.arange(T, dtype=torch.float32)[None, :] / 100
+            ret.put(bool(ok and torch.equal(out, want)))
+        else:
+            assert out is None and ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_local,chunks", [(2, 8, 4), (2, 5, 2), (3, 4, 1)])
+def test_synthesize_and_gather_pipeline_gloo(world, n_local, chunks):
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pipeline, args=(r, world, port, n_local, chunks, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get() is True
