@@ -248,6 +248,211 @@ __global__ void __launch_bounds__(MAXT, MINB) ltv_fir_kernel(FirParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant with 16 outputs per thread and packed FP32x2 FMAs (fma.rn.f32x2, sm_100 FFMA2).
+// The scalar kernel above sits at ~62 % of the FP32 peak: LDS.128 lands window / table values in
+// both register banks, so many 3-source FFMAs have all operands in one bank (a register-only
+// replica of its inner step reaches 73 %, the FFMA2 form 83 %, scratch/fir_pattern.cu).  Here the
+// accumulators are (a1[r], a2[r]) pairs, the table entries (G, E) pairs straight from LDS.128, and
+// each input value is duplicated into a pair once per step; 16 outputs per thread halve the shared
+// loads per FMA.  One warp per filter (32 threads x 16 outputs = P = 512), window of 5 chunks
+// rotated over a 5-step unrolled loop, inputs in a (chunk ^ (chunk>>3 & 3)) swizzle so the
+// stride-4-chunk lane pattern is conflict free.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
+__device__ __forceinline__ int swz4(int c) { return c ^ ((c >> 3) & 3); }
+
+// one 4-tap step; ROT: physical slot of logical chunk L is (L + ROT) % 5, the new (lowest) chunk is logical 0
+template <int ROT>
+__device__ __forceinline__ void fir16_step(u64 (&ch)[5][4], const float4& xn, const float4& t0, const float4& t1,
+                                           u64 (&acc)[16]) {
+    constexpr int p0 = ROT % 5;
+    ch[p0][0] = pack2(xn.x, xn.x); ch[p0][1] = pack2(xn.y, xn.y);
+    ch[p0][2] = pack2(xn.z, xn.z); ch[p0][3] = pack2(xn.w, xn.w);
+    const u64 ge[4] = {pack2(t0.x, t0.y), pack2(t0.z, t0.w), pack2(t1.x, t1.y), pack2(t1.z, t1.w)};
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int j = 3 + r - tt;                       // window index 0..18
+            ffma2(acc[r], ch[((j >> 2) + ROT) % 5][j & 3], ge[tt]);
+        }
+    }
+}
+
+// threads per job = P/16 (a multiple of 32).  smem per job as in ltv_fir_kernel (xs[2P] swizzled here).
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ltv_fir16_kernel(FirParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int P = p.P, T = p.T, nF = p.nF;
+    const int TPJ = P >> 4;
+    const int job = threadIdx.x / TPJ;
+    const int lt = threadIdx.x - job * TPJ;
+    const int b = blockIdx.y, f = blockIdx.x;
+    const int per_job = 6 * P + 8 + (P + (P >> 4) + 8);
+    float* xs = sm + job * per_job;
+    float4* xs4 = reinterpret_cast<float4*>(xs);
+    float* tabA = xs + 2 * P;
+    float* tabB = tabA + 2 * P + 8;
+    // second difference across frames d2[tp] = h_{g+1} - 2 h_g + h_{g-1}: (GA-GB, EA-EB) = (-w d2, d2) for the
+    // band fix-up; padded by one float per 16 taps so the stride-16 lane pattern is conflict free
+    float* d2s = tabB + 2 * P;
+    float4* ybuf4 = reinterpret_cast<float4*>(sm + p.njobs * per_job);  // [njobs][P/4] float4, swizzled
+
+    FirJob jb;
+    jb.x = job ? p.job[1].x : p.job[0].x;
+    jb.ir = job ? p.job[1].ir : p.job[0].ir;
+    jb.y = job ? p.job[1].y : p.job[0].y;
+    jb.L = job ? p.job[1].L : p.job[0].L;
+    const int L = jb.L, Mh = L / 2 + 1;
+    const int NS = (L + P - 1) / P;
+    const int i0 = lt << 4;
+    const float invP = 1.0f / (float)P;
+    const float* xrow = jb.x ? jb.x + (size_t)b * T : nullptr;
+    const float* irb = jb.ir + (size_t)b * nF * L;
+
+    u64 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0ull;
+
+    for (int s = 0; s < NS; ++s) {
+        const int g = f - s;
+        if (g < 0 || g > nF) continue;
+        job_barrier(job, TPJ);
+        const int mbase = g * P - P;
+        for (int c = lt; c < (P >> 1); c += TPJ) {
+            const int m = mbase + (c << 2);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m >= 0 && m < T) {
+                if (xrow) v = __ldg(reinterpret_cast<const float4*>(xrow + m));
+                else v = b2d::philox_uniform_pm1(p.seed, (unsigned long long)(p.utt_off + b), (uint32_t)(m >> 2));
+            }
+            xs4[swz4(c)] = v;
+        }
+        const float* hm = irb + (size_t)min(max(g - 1, 0), nF - 1) * L;
+        const float* h0 = irb + (size_t)min(max(g, 0), nF - 1) * L;
+        const float* hp = irb + (size_t)min(max(g + 1, 0), nF - 1) * L;
+        for (int tp = lt; tp < P; tp += TPJ) {
+            const int tau = s * P + tp;
+            float vm = 0.f, v0 = 0.f, vp = 0.f;
+            if (tau < L) { vm = __ldg(hm + tau); v0 = __ldg(h0 + tau); vp = __ldg(hp + tau); }
+            const float w = (float)tp * invP;
+            const float eA = vp - v0, eB = v0 - vm;
+            reinterpret_cast<float2*>(tabA)[tp] = make_float2(fmaf(-w, eA, v0), eA);
+            reinterpret_cast<float2*>(tabB)[tp] = make_float2(fmaf(-w, eB, v0), eB);
+            d2s[tp + (tp >> 4)] = eA - eB;
+        }
+        job_barrier(job, TPJ);
+
+        const float4* tA = reinterpret_cast<const float4*>(tabA);
+        const float4* tB = reinterpret_cast<const float4*>(tabB);
+        const int c0 = (P >> 2) - 1 + (lt << 2);  // chunk of logical q = P-4+i0 (step 0's new chunk)
+        const int sw = lt << 2;                   // steps < sw use the A tables (tau0 < i0)
+        const int nsteps = P >> 2;
+        u64 ch[5][4];
+        // logical chunks 1..4 before step 0 (logical L holds chunk c0 + L) -> physical slots 1..4 (ROT = 0)
+#pragma unroll
+        for (int Lc = 1; Lc < 5; ++Lc) {
+            const float4 v = xs4[swz4(c0 + Lc)];
+            ch[Lc][0] = pack2(v.x, v.x); ch[Lc][1] = pack2(v.y, v.y); ch[Lc][2] = pack2(v.z, v.z); ch[Lc][3] = pack2(v.w, v.w);
+        }
+#define B2D_FIR16_STEP(ROT, J)                                                        \
+        {                                                                             \
+            const float4* tp4 = ((step + (J)) < sw ? tA : tB) + 2 * (step + (J));     \
+            const float4 t0 = tp4[0], t1 = tp4[1];                                    \
+            const float4 xn = xs4[swz4(c0 - step - (J))];                             \
+            fir16_step<ROT>(ch, xn, t0, t1, acc);                                     \
+        }
+        int step = 0;
+        for (; step + 5 <= nsteps; step += 5) {
+            B2D_FIR16_STEP(0, 0)
+            B2D_FIR16_STEP(4, 1)
+            B2D_FIR16_STEP(3, 2)
+            B2D_FIR16_STEP(2, 3)
+            B2D_FIR16_STEP(1, 4)
+        }
+        // remainder (nsteps mod 5 in 0..4): the rotation continues 0, 4, 3, 2 from the loop's end state
+        if (step < nsteps) { B2D_FIR16_STEP(0, 0) }
+        if (step + 1 < nsteps) { B2D_FIR16_STEP(4, 1) }
+        if (step + 2 < nsteps) { B2D_FIR16_STEP(3, 2) }
+        if (step + 3 < nsteps) { B2D_FIR16_STEP(2, 3) }
+#undef B2D_FIR16_STEP
+        // ---- band fix-up: taps tau' in [i0, i0+r) belong to the A tables for output r ----
+#pragma unroll
+        for (int bb = 0; bb < 15; ++bb) {
+            const int tp = i0 + bb;
+            const float d2 = d2s[tp + (tp >> 4)];
+            const u64 dge = pack2(-((float)tp * invP) * d2, d2);
+#pragma unroll
+            for (int r = bb + 1; r < 16; ++r) {
+                const int q = P - 1 + r - bb;
+                const float xv = xs[(swz4(q >> 2) << 2) | (q & 3)];
+                ffma2(acc[r], pack2(xv, xv), dge);
+            }
+        }
+    }
+
+    float yv[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        float a1, a2;
+        unpack2(acc[r], a1, a2);
+        yv[r] = fmaf((float)(i0 + r - 1) * invP, a2, a1);
+    }
+    const int n0 = f * P - Mh + i0;
+    const bool vec_ok = ((n0 & 3) == 0) && n0 >= 0 && (n0 + 16) <= T;
+    if (jb.y) {
+        float* yrow = jb.y + (size_t)b * T;
+        if (vec_ok) {
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4)
+                b2d::st_global_v4(yrow + n0 + 4 * v4, make_float4(yv[4 * v4], yv[4 * v4 + 1], yv[4 * v4 + 2], yv[4 * v4 + 3]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (n0 + r >= 0 && n0 + r < T) yrow[n0 + r] = yv[r];
+        }
+    }
+    if (p.mix) {
+        if (p.njobs > 1) {
+            if (job == 1) {
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    ybuf4[swz4((lt << 2) + v4)] = make_float4(yv[4 * v4], yv[4 * v4 + 1], yv[4 * v4 + 2], yv[4 * v4 + 3]);
+            }
+            __syncthreads();
+        }
+        if (job == 0) {
+            float* mrow = p.mix + (size_t)b * T;
+            const float* arow = p.addend ? p.addend + (size_t)b * T : nullptr;
+            if (p.njobs > 1) {
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const float4 o = ybuf4[swz4((lt << 2) + v4)];
+                    yv[4 * v4] += o.x; yv[4 * v4 + 1] += o.y; yv[4 * v4 + 2] += o.z; yv[4 * v4 + 3] += o.w;
+                }
+            }
+            if (arow) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    if (n0 + r >= 0 && n0 + r < T) yv[r] += arow[n0 + r];
+            }
+            if (vec_ok) {
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    b2d::st_global_v4(mrow + n0 + 4 * v4, make_float4(yv[4 * v4], yv[4 * v4 + 1], yv[4 * v4 + 2], yv[4 * v4 + 3]));
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    if (n0 + r >= 0 && n0 + r < T) mrow[n0 + r] = yv[r];
+            }
+        }
+    }
+}
+
 // One thread per output sample, straight from the definition.  Any P / L.
 __global__ void ltv_fir_generic_kernel(const float* __restrict__ x, const float* __restrict__ ir, int L,
                                        float* __restrict__ y, int nF, int P, int T) {
@@ -283,6 +488,8 @@ int ltv_fir_tc_launch(const float* x1, const float* ir1, int taps1, float* y1, c
 // 4.20 ms against 1.26 ms -- with N = 8 columns every MMA re-reads its 4 KB Hankel operand from
 // shared memory for 16 kflop, so it is operand-bandwidth bound (~56 cycles per 128x8x8 MMA).
 static int g_fir_impl = 0;
+// CUDA-core variant: 0 = auto (16 outputs/thread + FFMA2 when the block size is a multiple of 512), 1 = 8 outputs/thread scalar
+static int g_fir_variant = 0;
 
 // internal entry (also used by the CombSub driver): mix = y1 (+ y2) (+ addend)
 int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
@@ -338,6 +545,21 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
         kern<<<dim3(ntiles, B), threads, smem, st>>>(p);
         return check_launch("ltv_fir");
     };
+    if (g_fir_variant != 1 && P % 512 == 0) {            // 16 outputs/thread, FFMA2 (one warp per filter at P = 512)
+        const int threads16 = njobs * (P / 16);
+        const size_t smem = (size_t)(njobs * (6 * P + 8 + P + (P >> 4) + 8) + P) * sizeof(float);
+        auto go16 = [&](auto kern) -> int {
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return fail((int)e, "ltv_fir16: smem attr: %s", cudaGetErrorString(e));
+            }
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            kern<<<dim3(ntiles, B), threads16, smem, st>>>(p);
+            return check_launch("ltv_fir16");
+        };
+        if (threads16 <= 64) return go16(ltv_fir16_kernel<64, 7>);
+        return go16(ltv_fir16_kernel<256, 1>);
+    }
     // register budget: 80/thread is spill-free; more resident CTAs hide the table-build prologue
     if (threads <= 128) return go(ltv_fir_kernel<128, 6>);
     if (threads <= 256) return go(ltv_fir_kernel<256, 3>);
@@ -347,8 +569,10 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
 }  // namespace b2d
 
 extern "C" int b2d_set_fir_impl(int impl) {
-    if (impl < 0 || impl > 2) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
-    b2d::g_fir_impl = impl;
+    // 0 auto, 1 CUDA cores (auto variant), 2 tensor cores, 3 CUDA cores forcing the 8-outputs/thread scalar kernel
+    if (impl < 0 || impl > 3) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
+    b2d::g_fir_impl = (impl == 3) ? 1 : impl;
+    b2d::g_fir_variant = (impl == 3) ? 1 : 0;
     return 0;
 }
 

@@ -116,7 +116,9 @@ int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1,
 /* Two implementations of the tiled kernel exist: CUDA cores (default; block size multiple of
  * 256) and tcgen05 tensor cores (3xTF32, block size 512; correct but operand-bandwidth bound and
  * ~3x slower on B200).  0 = automatic (CUDA cores), 1 = CUDA cores, 2 = tensor
- * cores.  Process-wide test/diagnostic knob. */
+ * cores, 3 = CUDA cores forcing the older 8-outputs-per-thread scalar-FFMA kernel (the default
+ * CUDA-core kernel for block sizes that are multiples of 512 uses 16 outputs per thread and packed
+ * fma.rn.f32x2).  Process-wide test/diagnostic knob. */
 int b2d_set_fir_impl(int impl);
 
 /* Same result by the plain one-thread-per-sample formula (any block size / tap count);
