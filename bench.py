@@ -284,14 +284,26 @@ class Runner:
             self.fixed.ctrls = full
 
     # the same through HOST buffers: pinned inputs -> H2D -> public module API -> D2H of the result
-    def step_e2e(self):
-        f0_x = self.f0_h.to(self.dev, non_blocking=True)
+    def step_e2e(self, chunks=4):
+        """public API with host buffers: HostPipeline (chunked upload | kernels | download) around the module's
+        forward; returns the event to synchronise on."""
+        from ddsp_svc_b200 import HostPipeline
+        if getattr(self, "_pipe", None) is None or self._pipe.chunks != chunks:
+            self._pipe = HostPipeline(self.dev, chunks=chunks)
+        host = {"f0": self.f0_h}
         if self.w["kind"] != "sinegen":
-            self.fixed.ctrls = self.syn.split_views(self.dense_h.to(self.dev, non_blocking=True), self.sm)
-        sig = self.step(f0_x)
-        self.out_h.copy_(sig, non_blocking=True)
-        if self.w["kind"] != "sinegen":
-            self.fixed.ctrls = self.ctrl_d
+            host["dense"] = self.dense_h
+
+        def fwd(d, lo, hi):
+            if self.w["kind"] == "sinegen":
+                return self.model(d["f0"][..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B + lo)
+            self.fixed.ctrls = self.syn.split_views(d["dense"], self.sm)
+            try:
+                return self.model(None, d["f0"], None, utterance_offset=self.rank * self.B + lo)[0]
+            finally:
+                self.fixed.ctrls = self.ctrl_d
+
+        return self._pipe.run(host, fwd, self.out_h)
 
     def kernels(self):
         """name -> callable launching exactly that kernel (inputs prepared beforehand)."""
@@ -347,6 +359,7 @@ def main():
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the waveform")
     ap.add_argument("--gather-chunks", type=int, default=4,
                     help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance chunks of the host-buffer pipeline (1 = serial)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -419,8 +432,8 @@ def main():
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            run.step_e2e()
-            b.record()
+            run.step_e2e(args.e2e_chunks).synchronize()
+            b.record()                     # recorded on the main stream, which waits for the download stream
             b.synchronize()
             if i > 0:
                 ee.append(a.elapsed_time(b))
@@ -474,7 +487,9 @@ def main():
                                  "Sins/CombSub are FP32/SFU-issue bound by construction (see DESIGN.md)"},
             "e2e": {"value": samples_step / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": run.h2d, "d2h_bytes_per_step": run.out_h.numel() * 4,
-                    "what": "pinned host f0+controls -> H2D -> module forward (public API) -> D2H of the waveform"},
+                    "what": "pinned host f0+controls -> H2D -> module forward -> D2H of the waveform, through "
+                            "ddsp_svc_b200.HostPipeline (%d utterance chunks; upload, kernels and download overlap)"
+                            % args.e2e_chunks},
             "gpu_launches": launches,
             "clocks": clk,
         }
