@@ -128,6 +128,17 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload, kernel_label):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture (profiles/r1_traffic.json); None when no capture is recorded for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            ent = json.load(f).get(workload, {})
+        return ent.get("dram_bytes_per_launch") if ent.get("bench_kernel") == kernel_label else None
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -445,12 +456,13 @@ def main():
         reps = max(5, min(args.steps, 20))
         for name, fn in run.kernels().items():
             ts = []
+            fn()                               # untimed: first use of this call path
             for _ in range(reps):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); fn(); b.record(); b.synchronize()
                 ts.append(a.elapsed_time(b))
-            kt[name] = sum(ts) / len(ts)
+            kt[name] = statistics.median(ts)   # average launch duration, robust to a stray slow launch
 
     # ---- reduce over ranks: max device time ----
     if world > 1:
@@ -480,7 +492,7 @@ def main():
                        "l2": "flushed between steps (256 MiB memset, untimed); per-step CUDA events summed",
                        "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kt,
                          "whole_path_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None,
                          "note": "achieved = algorithmic bytes of the whole path / duration of the dominant kernel; "

@@ -10,11 +10,12 @@
 // cross-lane reduction is needed.
 //
 // The kernel is MUFU (sin/cos SFU) bound, so the harmonic set is factored as
-//   h = a + 32 b,  a = 1..32 (anchors), b = 0..3 (bases):
-//   sin(h p) = sin(a p) cos(32 b p) + cos(a p) sin(32 b p)
-// which needs 2 MUFU per anchor + 2 per base (70 per sample for H = 128 instead of 128) and
-// 3 FP32 ops per harmonic:  amp = fma(dA, frac, A);  P_b += sin(a p) * amp;  Q_b += cos(a p) * amp;
-// result = sum_b P_b cos(32 b p) + Q_b sin(32 b p).
+//   h = a + 16 b,  a = 1..16 (anchors), b = 0..7 (bases):
+//   sin(h p) = sin(a p) cos(16 b p) + cos(a p) sin(16 b p)
+// which needs 2 MUFU per anchor + 2 per base (46 per sample for H = 128 instead of 128; the first
+// version used 32 anchors x 4 bases = 70 and was SFU bound at 0.31 ms) and 3 FP32 ops per harmonic:
+//   amp = fma(dA, frac, A);  P_b += sin(a p) * amp;  Q_b += cos(a p) * amp;
+// result = sum_b P_b cos(16 b p) + Q_b sin(16 b p).
 //
 // The per-sample phase is evaluated in fp64 from the frame-rate scan (phase_scan.cu):
 //   x = S_k + ((j+1) f_k + (f_{k+1}-f_k) j (j+1) / (2P)) / sr,  wrapped, rounded to fp32,
@@ -25,7 +26,9 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kFramesPerCta = 8;
-constexpr int kGroup = 128;  // harmonics per group = 32 anchors x 4 bases
+constexpr int kGroup = 128;  // harmonics per group = 16 anchors x 8 bases
+constexpr int kNA = 16;      // anchors
+constexpr int kNBmax = 8;    // bases per group
 
 struct BankParams {
     const float* f0;
@@ -43,58 +46,79 @@ struct BankParams {
 // slot of 0-based harmonic index hh inside a padded row: [group][anchor][base]
 __device__ __forceinline__ int slot_of(int hh) {
     int g = hh >> 7, r = hh & 127;
-    return (g << 7) + ((r & 31) << 2) + (r >> 5);
+    return (g << 7) + ((r & (kNA - 1)) * kNBmax) + (r / kNA);
 }
 
-// One group of (up to) 128 harmonics for 4 samples.  TRIVIAL0: the group's base-0 rotation
-// is the identity (group 0), saving the Q_0 accumulator.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// One group of (up to) 128 harmonics for 4 samples.  NB = bases actually present (1..8).
+// Packed FP32x2 FMAs (sm_100 FFMA2): the amplitudes of two neighbouring bases are interpolated by
+// one instruction, and (P_b, Q_b) += (sin, cos) * amp is one instruction, so a harmonic costs 1.5
+// issue slots instead of 3 (the kernel is issue bound, measured 78 % issue-active).
 template <int NB, bool TRIVIAL0>
 __device__ __forceinline__ void bank_group(const float* __restrict__ arow, const float* __restrict__ drow,
                                            int group, const float (&x32)[4], const float (&phase)[4],
                                            const float (&frac)[4], float (&acc)[4]) {
-    float Pb[4][NB], Qb[4][NB];
+    constexpr int NP = (NB + 1) / 2;          // base pairs
+    u64 PQ[4][2 * NP];
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) Pb[s][b] = Qb[s][b] = 0.f;
+        for (int b = 0; b < 2 * NP; ++b) PQ[s][b] = 0ull;
 
     const float4* a4 = reinterpret_cast<const float4*>(arow + group * kGroup);
     const float4* d4 = reinterpret_cast<const float4*>(drow + group * kGroup);
     const float hbase = (float)(group * kGroup);
 
-#pragma unroll 4
-    for (int a = 0; a < 32; ++a) {
-        const float4 A = a4[a], D = d4[a];
-        const float Aa[4] = {A.x, A.y, A.z, A.w}, Da[4] = {D.x, D.y, D.z, D.w};
+#pragma unroll 2
+    for (int a = 0; a < kNA; ++a) {
+        u64 Ap[4], Dp[4];
+        {
+            const float4 A0 = a4[2 * a], D0 = d4[2 * a];
+            Ap[0] = pack2(A0.x, A0.y); Ap[1] = pack2(A0.z, A0.w);
+            Dp[0] = pack2(D0.x, D0.y); Dp[1] = pack2(D0.z, D0.w);
+            if (NB > 4) {
+                const float4 A1 = a4[2 * a + 1], D1 = d4[2 * a + 1];
+                Ap[2] = pack2(A1.x, A1.y); Ap[3] = pack2(A1.z, A1.w);
+                Dp[2] = pack2(D1.x, D1.y); Dp[3] = pack2(D1.z, D1.w);
+            }
+        }
         const float af = (float)(a + 1);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             float sa, ca;
             __sincosf(af * phase[s], &sa, &ca);
+            const u64 sc = pack2(sa, ca), fr = pack2(frac[s], frac[s]);
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float amp = fmaf(Da[b], frac[s], Aa[b]);
-                Pb[s][b] = fmaf(sa, amp, Pb[s][b]);
-                if (!(TRIVIAL0 && b == 0)) Qb[s][b] = fmaf(ca, amp, Qb[s][b]);
+            for (int bp = 0; bp < NP; ++bp) {
+                float amp0, amp1;
+                unpack2(ffma2(Dp[bp], fr, Ap[bp]), amp0, amp1);        // amplitudes of bases 2bp, 2bp+1
+                PQ[s][2 * bp] = ffma2(sc, pack2(amp0, amp0), PQ[s][2 * bp]);
+                if (2 * bp + 1 < NB) PQ[s][2 * bp + 1] = ffma2(sc, pack2(amp1, amp1), PQ[s][2 * bp + 1]);
             }
         }
     }
-    // rotate each base by (hbase + 32 b) * phase; the rotation angle is reduced exactly in
+    // rotate each base by (hbase + 16 b) * phase; the rotation angle is reduced exactly in
     // cycles (fma) before the SFU call because it reaches ~100 revolutions.
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
+            float Pv, Qv;
+            unpack2(PQ[s][b], Pv, Qv);
             if (TRIVIAL0 && b == 0) {
-                acc[s] += Pb[s][0];
+                acc[s] += Pv;
             } else {
-                const float hb = hbase + 32.f * (float)b;
+                const float hb = hbase + (float)(kNA * b);
                 const float n = rintf(hb * x32[s]);
                 const float r = fmaf(hb, x32[s], -n);
                 float so, co;
                 __sincosf(B2D_TWO_PI_F * r, &so, &co);
-                acc[s] = fmaf(Pb[s][b], co, acc[s]);
-                acc[s] = fmaf(Qb[s][b], so, acc[s]);
+                acc[s] = fmaf(Pv, co, acc[s]);
+                acc[s] = fmaf(Qv, so, acc[s]);
             }
         }
     }
@@ -188,8 +212,8 @@ __global__ void __launch_bounds__(kThreads, 4) sins_bank_kernel(BankParams p) {
         if (!MULTI) {
             bank_group<NB, true>(arow, drow, 0, x32, phase, frac, acc);
         } else {
-            bank_group<4, true>(arow, drow, 0, x32, phase, frac, acc);
-            for (int g = 1; g < G; ++g) bank_group<4, false>(arow, drow, g, x32, phase, frac, acc);
+            bank_group<kNBmax, true>(arow, drow, 0, x32, phase, frac, acc);
+            for (int g = 1; g < G; ++g) bank_group<kNBmax, false>(arow, drow, g, x32, phase, frac, acc);
         }
         b2d::st_global_v4(out + off, make_float4(acc[0], acc[1], acc[2], acc[3]));
     }
@@ -235,12 +259,16 @@ extern "C" int b2d_sins_bank(const float* f0_frames, const double* frame_phase, 
     const size_t smem = (size_t)((kFramesPerCta + 1) * HP + kFramesPerCta * HP + (kFramesPerCta + 1) * Hraw) * 4 +
                         kFramesPerCta * 8 + (kFramesPerCta + 1) * 4 + 16;
     cudaStream_t st = (cudaStream_t)stream;
-    if (G > 1) return launch<4, true>(p, B, smem, st);
-    const int nb = (n_harmonics + 31) / 32;
+    if (G > 1) return launch<kNBmax, true>(p, B, smem, st);
+    const int nb = (n_harmonics + kNA - 1) / kNA;
     switch (nb) {
         case 1: return launch<1, false>(p, B, smem, st);
         case 2: return launch<2, false>(p, B, smem, st);
         case 3: return launch<3, false>(p, B, smem, st);
-        default: return launch<4, false>(p, B, smem, st);
+        case 4: return launch<4, false>(p, B, smem, st);
+        case 5: return launch<5, false>(p, B, smem, st);
+        case 6: return launch<6, false>(p, B, smem, st);
+        case 7: return launch<7, false>(p, B, smem, st);
+        default: return launch<8, false>(p, B, smem, st);
     }
 }

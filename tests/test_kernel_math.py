@@ -4,7 +4,7 @@ algorithms (so a GPU parity failure can only be an implementation slip, not a de
 
 * ltv_fir.cu   : tile f / segment s / "A"-"B" table switch + band fix-up + (i-1)/P recombination
 * ir_build.cu  : even/odd-bin split of the inverse real DFT, t <-> M-1-t pairing, causal roll
-* sins_bank.cu : harmonic h = a + 32 b factorisation with per-base rotation
+* sins_bank.cu : harmonic h = a + 16 b factorisation with per-base rotation
 """
 import numpy as np
 import pytest
@@ -112,11 +112,11 @@ def test_bank_anchor_base_factorisation(H):
     got = np.zeros(50)
     G = (H + 127) // 128
     for g in range(G):
-        for b in range(4):
-            hb = 128 * g + 32 * b
+        for b in range(8):
+            hb = 128 * g + 16 * b
             Pb = np.zeros(50)
             Qb = np.zeros(50)
-            for a in range(1, 33):
+            for a in range(1, 17):
                 h = hb + a
                 if h > H:
                     continue
