@@ -368,7 +368,9 @@ def main():
     ap.add_argument("--workload", default="sins", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the waveform")
-    ap.add_argument("--gather-chunks", type=int, default=4,
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = the FIR kernel stores the waveform into rank 0's peer-mapped buffer; 'nccl' = gather")
+    ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance chunks of the host-buffer pipeline (1 = serial)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
@@ -399,10 +401,24 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     n_chunks = args.gather_chunks
+    peer = None
+    if do_gather and args.gather == "peer" and w["kind"] == "sins":
+        try:                                   # rank 0's buffer peer-mapped on every rank (NVLink)
+            peer = sharding.PeerGather(B, T, dev, dst=0)
+        except Exception as e:                 # symmetric memory unavailable: use the NCCL gather
+            if rank == 0:
+                print("peer gather unavailable (%s); using NCCL" % (str(e).splitlines()[0][:120],), file=sys.stderr)
+            peer = None
+    gather_mode = "none" if not do_gather else ("peer-mapped stores over NVLink from the FIR kernel + device barrier"
+                                                if peer is not None else "NCCL gather, %d chunk(s)" % n_chunks)
 
     def step():
         if not do_gather:
             return run.step()
+        if peer is not None:
+            sig = run.model(None, run.f0_d, None, utterance_offset=rank * B, signal_out=peer.my_rows)[0]
+            peer.finish()
+            return sig
         if n_chunks <= 1:
             sig = run.step()
             sharding.gather_waveform(sig.reshape(B, -1), world * B, dst=0)
@@ -487,8 +503,7 @@ def main():
                        "samples_per_utterance": T, "noise": "in-kernel Philox4x32-10",
                        "outputs": "signal+harmonic+noise" if w["kind"] in ("sins", "combsub") else "signal",
                        "parallelism": "batch-sharded x%d%s" % (
-                           world, (", NCCL gather of the waveform to rank 0 inside the step (%d chunks, overlapped with synthesis)"
-                                   % n_chunks) if do_gather else ""),
+                           world, (", waveform gathered on rank 0 inside the step: " + gather_mode) if do_gather else ""),
                        "l2": "flushed between steps (256 MiB memset, untimed); per-step CUDA events summed",
                        "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

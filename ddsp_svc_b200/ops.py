@@ -161,8 +161,11 @@ def ltv_fir(x, ir, block, seed=0, utterance_offset=0, generic=False):
 
 
 def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sampling_rate, noise_in=None,
-               seed=0, utterance_offset=0, infer=True, want_parts=True):
-    """Whole Sins DSP after Unit2Control -> (signal, harmonic, noise) [B, T] each."""
+               seed=0, utterance_offset=0, infer=True, want_parts=True, signal_out=None):
+    """Whole Sins DSP after Unit2Control -> (signal, harmonic, noise) [B, T] each.
+    ``signal_out``: optional preallocated [B, T] fp32 CUDA tensor for the mixed signal; it may live in
+    another GPU's memory (peer-mapped, see sharding.PeerGather): the FIR kernel then writes the
+    waveform straight over NVLink."""
     f0 = _frames_2d(f0_frames)
     B, nF = f0.shape
     _need_cuda_f32("frame_phase", frame_phase, torch.float64)
@@ -183,7 +186,13 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
     L = _lib.lib()
     ws_bytes = L.b2d_sins_workspace_bytes(B, nF, int(block), Ma, Mn)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    signal = torch.empty(B, T, dtype=torch.float32, device=dev)
+    if signal_out is not None:
+        _need_cuda_f32("signal_out", signal_out)
+        if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
+            raise ValueError("signal_out must be a contiguous [B, T] tensor")
+        signal = signal_out
+    else:
+        signal = torch.empty(B, T, dtype=torch.float32, device=dev)
     harmonic = torch.empty(B, T, dtype=torch.float32, device=dev) if want_parts else None
     noise = torch.empty(B, T, dtype=torch.float32, device=dev) if (want_parts or Ma != Mn) else None
     ta, tn = dft_tables(Ma, dev), dft_tables(Mn, dev)

@@ -131,3 +131,28 @@ class _null_ctx:
 
     def __exit__(self, *a):
         return False
+
+
+class PeerGather:
+    """Gather without a gather: rank ``dst`` owns the [n_global, T] result in symmetric memory and every
+    rank holds a tensor view of ITS rows of that buffer, mapped over NVLink (CUDA peer / fabric
+    handles via torch symmetric memory).  Passing ``my_rows`` as the synthesizer's ``signal_out`` makes
+    the last kernel of the path store the waveform directly into rank ``dst``'s HBM, so the transfer
+    overlaps the whole kernel instead of following it.  ``finish()`` is a device-side barrier over the
+    group (stream ordered): after it, ``result`` on ``dst`` holds every rank's rows.
+    """
+
+    def __init__(self, n_local, n_samples, device, dst=0, group=None, dtype=torch.float32):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.dst, self.rank = dst, rank
+        # symmetric allocation: every rank allocates the same shape; only dst's copy is the destination
+        self._local = symm_mem.empty(world * n_local, n_samples, dtype=dtype, device=device)
+        self._hdl = symm_mem.rendezvous(self._local, self.group)
+        self.my_rows = self._hdl.get_buffer(dst, (n_local, n_samples), dtype, rank * n_local * n_samples)
+        self.result = self._local if rank == dst else None
+
+    def finish(self):
+        self._hdl.barrier()
+        return self.result

@@ -73,9 +73,10 @@ class Sins(_SynthBase):
         self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _reference_unit2ctrl(n_unit, n_spk, split_map)
 
     def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, initial_phase=None,
-                infer=True, max_upsample_dim=32, noise=None, utterance_offset=0):
+                infer=True, max_upsample_dim=32, noise=None, utterance_offset=0, signal_out=None):
         """units_frames B x n_frames x n_unit; f0_frames B x n_frames x 1; volume_frames B x n_frames x 1.
-        ``max_upsample_dim`` only chunks the reference's temporaries and has no effect here."""
+        ``max_upsample_dim`` only chunks the reference's temporaries and has no effect here.
+        ``signal_out``: optional preallocated [B, T] destination of ``signal`` (may be peer-mapped memory)."""
         sr, block = self._scalars()
         frame_phase, phase_frames = ops.phase_scan(f0_frames, block, sr, initial_phase, infer)
         ctrls, hidden = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id=spk_id,
@@ -84,7 +85,7 @@ class Sins(_SynthBase):
         signal, harmonic, noise_out = ops.sins_synth(
             f0_frames, frame_phase, ctrls["amplitudes"], ctrls["group_delay"], ctrls["noise_magnitude"], block, sr,
             noise_in=noise, seed=0 if noise is not None else _host_seed(), utterance_offset=utterance_offset,
-            infer=infer)
+            infer=infer, signal_out=signal_out)
         return signal, hidden, (harmonic, noise_out)
 
 
