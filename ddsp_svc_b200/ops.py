@@ -254,7 +254,7 @@ def _same_stride(named, B, nF):
 
 
 def combsub_synth(f0_frames, frame_phase, c_group_delay, c_harmonic, c_noise, block, sampling_rate, noise_in=None,
-                  seed=0, utterance_offset=0, infer=True):
+                  seed=0, utterance_offset=0, infer=True, signal_out=None):
     """Whole old-CombSub DSP after Unit2Control -> (signal, harmonic, noise) [B, T] each."""
     f0 = _frames_2d(f0_frames)
     B, nF = f0.shape
@@ -270,6 +270,11 @@ def combsub_synth(f0_frames, frame_phase, c_group_delay, c_harmonic, c_noise, bl
     ws_bytes = L.b2d_combsub_workspace_bytes(B, nF, int(block), Ma, Mh, Mn)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     signal, harmonic, noise = (torch.empty(B, T, dtype=torch.float32, device=dev) for _ in range(3))
+    if signal_out is not None:
+        _need_cuda_f32("signal_out", signal_out)
+        if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
+            raise ValueError("signal_out must be a contiguous [B, T] tensor")
+        signal = signal_out
     rc = L.b2d_combsub_synth(f0.data_ptr(), frame_phase.data_ptr(), cg.data_ptr(), ch.data_ptr(), cn.data_ptr(),
                              stride, _ptr(noise_in), int(seed), int(utterance_offset), dft_tables(Ma, dev).data_ptr(),
                              dft_tables(Mh, dev).data_ptr(), dft_tables(Mn, dev).data_ptr(), B, nF, int(block), Ma,
@@ -294,7 +299,8 @@ def superfast_scan(f0_frames, block, sampling_rate):
     return ws, phase_frames
 
 
-def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None, seed=0, utterance_offset=0):
+def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None, seed=0, utterance_offset=0,
+                    signal_out=None):
     B, nF = c_hm.shape[0], c_hm.shape[1]
     (hm, hp, nm, npz), stride = _same_stride([("harmonic_magnitude", c_hm), ("harmonic_phase", c_hp),
                                               ("noise_magnitude", c_nm), ("noise_phase", c_np)], B, nF)
@@ -304,7 +310,13 @@ def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None
     if noise_in is not None:
         _need_cuda_f32("noise_in", noise_in)
         noise_in = noise_in.reshape(B, T).contiguous()
-    signal = torch.empty(B, T, dtype=torch.float32, device=hm.device)
+    if signal_out is not None:
+        _need_cuda_f32("signal_out", signal_out)
+        if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
+            raise ValueError("signal_out must be a contiguous [B, T] tensor")
+        signal = signal_out
+    else:
+        signal = torch.empty(B, T, dtype=torch.float32, device=hm.device)
     rc = _lib.lib().b2d_superfast_synth(ws.data_ptr(), hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), npz.data_ptr(),
                                         stride, _ptr(noise_in), int(seed), int(utterance_offset), B, nF, int(block),
                                         int(win_length), signal.data_ptr(), _stream())

@@ -105,7 +105,7 @@ class CombSub(_SynthBase):
         self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _reference_unit2ctrl(n_unit, n_spk, split_map)
 
     def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, initial_phase=None,
-                infer=True, noise=None, utterance_offset=0, **kwargs):
+                infer=True, noise=None, utterance_offset=0, signal_out=None, **kwargs):
         sr, block = self._scalars()
         frame_phase, phase_frames = ops.phase_scan(f0_frames, block, sr, initial_phase, infer)
         ctrls, hidden = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id=spk_id,
@@ -114,7 +114,7 @@ class CombSub(_SynthBase):
         signal, harmonic, noise_out = ops.combsub_synth(
             f0_frames, frame_phase, ctrls["group_delay"], ctrls["harmonic_magnitude"], ctrls["noise_magnitude"],
             block, sr, noise_in=noise, seed=0 if noise is not None else _host_seed(),
-            utterance_offset=utterance_offset, infer=infer)
+            utterance_offset=utterance_offset, infer=infer, signal_out=signal_out)
         return signal, hidden, (harmonic, noise_out)
 
 
@@ -147,7 +147,7 @@ class CombSubSuperFast(_SynthBase):
         return c
 
     def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, aug_shift=None,
-                initial_phase=None, infer=True, noise=None, utterance_offset=0, **kwargs):
+                initial_phase=None, infer=True, noise=None, utterance_offset=0, signal_out=None, **kwargs):
         """``initial_phase`` is accepted and ignored, like the reference (ddsp/vocoder.py:653-661)."""
         sr, block, win = self._scalars()
         ws, phase_frames = ops.superfast_scan(f0_frames, block, sr)
@@ -157,7 +157,7 @@ class CombSubSuperFast(_SynthBase):
         signal = ops.superfast_synth(ws, ctrls["harmonic_magnitude"], ctrls["harmonic_phase"],
                                      ctrls["noise_magnitude"], ctrls["noise_phase"], block, win, noise_in=noise,
                                      seed=0 if noise is not None else _host_seed(),
-                                     utterance_offset=utterance_offset)
+                                     utterance_offset=utterance_offset, signal_out=signal_out)
         return signal, hidden, (signal, signal)
 
 
