@@ -368,8 +368,10 @@ def main():
     ap.add_argument("--workload", default="sins", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the waveform")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N>1: 'peer' = the FIR kernel stores the waveform into rank 0's peer-mapped buffer; 'nccl' = gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-copy", "nccl"],
+                    help="N>1: 'peer' = the FIR kernel stores the waveform into rank 0's peer-mapped buffer; "
+                         "'peer-copy' = chunked synthesis + copy-engine DMA into that buffer; 'nccl' = gather; "
+                         "'auto' = peer for N<=4, nccl for N=8 (measured)")
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance chunks of the host-buffer pipeline (1 = serial)")
@@ -402,23 +404,31 @@ def main():
 
     n_chunks = args.gather_chunks
     peer = None
-    if do_gather and args.gather == "peer" and w["kind"] == "sins":
+    mode = args.gather
+    if mode == "auto":     # measured on B200 (ms/step, peer stores vs NCCL gather): N=2 1.73/1.86, N=4 1.77/2.01, N=8 2.57/2.28
+        mode = "peer" if world <= 4 else "nccl"
+    if do_gather and mode in ("peer", "peer-copy") and w["kind"] == "sins":
         try:                                   # rank 0's buffer peer-mapped on every rank (NVLink)
             peer = sharding.PeerGather(B, T, dev, dst=0)
         except Exception as e:                 # symmetric memory unavailable: use the NCCL gather
             if rank == 0:
                 print("peer gather unavailable (%s); using NCCL" % (str(e).splitlines()[0][:120],), file=sys.stderr)
             peer = None
-    gather_mode = "none" if not do_gather else ("peer-mapped stores over NVLink from the FIR kernel + device barrier"
-                                                if peer is not None else "NCCL gather, %d chunk(s)" % n_chunks)
+    if peer is None and mode in ("peer", "peer-copy"):
+        mode = "nccl"
+    gather_mode = {"peer": "peer-mapped stores over NVLink from the FIR kernel + device barrier",
+                   "peer-copy": "%d chunks, copy-engine DMA of finished chunks into rank 0's peer-mapped buffer" % max(n_chunks, 2),
+                   "nccl": "NCCL gather, %d chunk(s)" % n_chunks}[mode] if do_gather else "none"
 
     def step():
         if not do_gather:
             return run.step()
-        if peer is not None:
+        if peer is not None and mode == "peer":
             sig = run.model(None, run.f0_d, None, utterance_offset=rank * B, signal_out=peer.my_rows)[0]
             peer.finish()
             return sig
+        if peer is not None:
+            return sharding.synthesize_and_push(run.step_rows, peer, B, dev, chunks=max(n_chunks, 2))
         if n_chunks <= 1:
             sig = run.step()
             sharding.gather_waveform(sig.reshape(B, -1), world * B, dst=0)

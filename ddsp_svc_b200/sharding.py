@@ -156,3 +156,27 @@ class PeerGather:
     def finish(self):
         self._hdl.barrier()
         return self.result
+
+    def push_rows(self, lo, hi, rows, stream):
+        """Copy finished local rows [lo, hi) into rank dst's buffer with the copy engine (DMA over NVLink)
+        on ``stream``; no SM takes part, so it overlaps the synthesis of the next chunk."""
+        with torch.cuda.stream(stream):
+            self.my_rows[lo:hi].copy_(rows, non_blocking=True)
+            rows.record_stream(stream)
+
+
+def synthesize_and_push(synth_chunk, peer, n_local, device, chunks=4):
+    """Chunked synthesis; each finished chunk is DMA-copied into rank dst's peer-mapped buffer on a side
+    stream while the next chunk is being synthesized.  Returns the gathered tensor on dst after a
+    device barrier."""
+    main = torch.cuda.current_stream(device)
+    comm = _comm_stream(device)
+    comm.wait_stream(main)
+    for lo, hi in _chunk_bounds(n_local, chunks):
+        part = synth_chunk(lo, hi)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        comm.wait_event(ev)
+        peer.push_rows(lo, hi, part, comm)
+    main.wait_stream(comm)
+    return peer.finish()
