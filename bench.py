@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-copy", "nccl"],
                     help="N>1: 'peer' = the FIR kernel stores the waveform into rank 0's peer-mapped buffer; "
                          "'peer-copy' = chunked synthesis + copy-engine DMA into that buffer; 'nccl' = gather; "
-                         "'auto' = peer for N<=4, nccl for N=8 (measured)")
+                         "'auto' = peer for N<=4, peer-copy with 2 chunks for N=8 (measured)")
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance chunks of the host-buffer pipeline (1 = serial)")
@@ -405,8 +405,12 @@ def main():
     n_chunks = args.gather_chunks
     peer = None
     mode = args.gather
-    if mode == "auto":     # measured on B200 (ms/step, peer stores vs NCCL gather): N=2 1.73/1.86, N=4 1.77/2.01, N=8 2.57/2.28
-        mode = "peer" if world <= 4 else "nccl"
+    if mode == "auto":
+        # measured on B200, ms/step (peer stores | 2-chunk DMA push | NCCL gather): N=2 1.73 | - | 1.86,
+        # N=4 1.77 | 1.91 | 2.01, N=8 2.57 | 2.04 | 2.28
+        mode = "peer" if world <= 4 else "peer-copy"
+        if mode == "peer-copy":
+            n_chunks = 2
     if do_gather and mode in ("peer", "peer-copy") and w["kind"] == "sins":
         try:                                   # rank 0's buffer peer-mapped on every rank (NVLink)
             peer = sharding.PeerGather(B, T, dev, dst=0)
