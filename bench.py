@@ -36,6 +36,8 @@ WORKLOADS = {
                       label="CombSubSuperFast forward DSP (configs/combsub.yaml), B=32 x 10 s, win 2048 (BASELINE configs[2])"),
     "sinegen": dict(kind="sinegen", B=64, sec=10, dim=9,
                     label="nsf_hifigan SineGen, B=64 x 10 s, 9 harmonics (BASELINE configs[4])"),
+    "srcmod": dict(kind="srcmod", B=64, sec=10, dim=9,
+                   label="nsf_hifigan SourceModuleHnNSF = SineGen + tanh(Linear(9->1)) fused, B=64 x 10 s (SURVEY 8f)"),
 }
 
 
@@ -53,6 +55,8 @@ def algorithmic_bytes(w, nF):
         return 4 * B * nF * (1 + 4 * (w["win"] // 2 + 1)) + 4 * B * T
     if w["kind"] == "sinegen":
         return 4 * B * nF + 4 * B * T * w["dim"]
+    if w["kind"] == "srcmod":
+        return 4 * B * nF + 4 * B * T
     raise ValueError(w["kind"])
 
 
@@ -78,6 +82,10 @@ def oracle_forward(w, f0, ctrls):
         return tp.combsub_forward(f0, ctrls, SR, P)
     if k == "superfast":
         return tp.superfast_forward(f0, ctrls, SR, P, w["win"])
+    if k == "srcmod":
+        import torch
+        g = torch.Generator().manual_seed(5)
+        return tp.source_module_forward(f0[..., 0], P, SR, torch.randn(1, w["dim"], generator=g) / 3, torch.zeros(1), w["dim"] - 1)
     return tp.sinegen_forward(f0[..., 0], P, SR, w["dim"] - 1)
 
 
@@ -242,7 +250,8 @@ class Runner:
     """Per-workload device state: how to run one step and how to time each kernel alone."""
 
     def __init__(self, w, dev, rank, torch):
-        from ddsp_svc_b200 import CombSub, CombSubSuperFast, FixedControls, SineGen, Sins, ops, synthetic as syn
+        from ddsp_svc_b200 import (CombSub, CombSubSuperFast, FixedControls, SineGen, SourceModuleHnNSF, Sins, ops,
+                                   synthetic as syn)
         self.w, self.dev, self.rank, self.torch, self.ops, self.syn = w, dev, rank, torch, ops, syn
         B = self.B = w["B"]
         nF = self.nF = syn.n_frames_for(w["sec"], SR, P)
@@ -252,10 +261,15 @@ class Runner:
         self.f0_d = self.f0_h.to(dev)
         self.h2d = self.f0_h.numel() * 4
         k = w["kind"]
-        if k == "sinegen":
+        self.sg = k in ("sinegen", "srcmod")           # f0-only excitation generators
+        self.width = w["dim"] if k == "sinegen" else 1
+        if self.sg:
             self.rand_ini = torch.rand(w["dim"]); self.rand_ini[0] = 0
-            self.model = SineGen(SR, harmonic_num=w["dim"] - 1)
-            self.out_h = torch.empty(B, self.T, w["dim"], dtype=torch.float32).pin_memory()
+            if k == "sinegen":
+                self.model = SineGen(SR, harmonic_num=w["dim"] - 1)
+            else:
+                self.model = SourceModuleHnNSF(SR, harmonic_num=w["dim"] - 1).to(dev).eval()
+            self.out_h = torch.empty(B, self.T, self.width, dtype=torch.float32).pin_memory()
             return
         self.dense_h = syn.make_ctrl(B, nF, self.sm, seed=7 + rank)[0].pin_memory()
         self.dense_d = self.dense_h.to(dev)
@@ -273,18 +287,18 @@ class Runner:
     # one pass of the hot path with inputs resident in HBM; returns the waveform to gather
     def step(self, f0=None):
         f0 = self.f0_d if f0 is None else f0
-        if self.w["kind"] == "sinegen":
+        if self.sg:
             return self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B)
         return self.model(None, f0, None, utterance_offset=self.rank * self.B)[0]
 
     # rows [lo, hi) of the local batch (for the chunked synth+gather pipeline) -> [hi-lo, row_len]
     @property
     def row_len(self):
-        return self.T * (self.w["dim"] if self.w["kind"] == "sinegen" else 1)
+        return self.T * self.width
 
     def step_rows(self, lo, hi):
         f0 = self.f0_d[lo:hi]
-        if self.w["kind"] == "sinegen":
+        if self.sg:
             out = self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B + lo)
             return out.reshape(hi - lo, -1)
         full = self.fixed.ctrls
@@ -302,11 +316,11 @@ class Runner:
         if getattr(self, "_pipe", None) is None or self._pipe.chunks != chunks:
             self._pipe = HostPipeline(self.dev, chunks=chunks)
         host = {"f0": self.f0_h}
-        if self.w["kind"] != "sinegen":
+        if not self.sg:
             host["dense"] = self.dense_h
 
         def fwd(d, lo, hi):
-            if self.w["kind"] == "sinegen":
+            if self.sg:
                 return self.model(d["f0"][..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B + lo)
             self.fixed.ctrls = self.syn.split_views(d["dense"], self.sm)
             try:
@@ -325,6 +339,10 @@ class Runner:
         k = w["kind"]
         if k == "sinegen":
             return {"sinegen(scan+stream)": lambda: ops.sinegen(f0[..., 0], P, SR, w["dim"], self.rand_ini, seed=1)}
+        if k == "srcmod":
+            lw, lb = self.model.l_linear.weight, float(self.model.l_linear.bias)
+            return {"source_module(scan+stream)": lambda: ops.source_module(f0[..., 0], P, SR, w["dim"], self.rand_ini,
+                                                                            lw, lb, seed=1)}
         if k == "superfast":
             ws, _ = ops.superfast_scan(f0, P, SR)
             return {"superfast_scan": lambda: ops.superfast_scan(f0, P, SR),
@@ -375,6 +393,8 @@ def main():
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance chunks of the host-buffer pipeline (1 = serial)")
+    ap.add_argument("--sinegen-impl", default="auto", choices=["auto", "v1", "v2", "v2p"],
+                    help="A/B switch for the SineGen / source-module kernel (ops.set_sinegen_impl)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -398,6 +418,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     run = Runner(w, dev, rank, torch)
+    if args.sinegen_impl != "auto":
+        run.ops.set_sinegen_impl(args.sinegen_impl)
     B, nF, T = run.B, run.nF, run.T
     do_gather = world > 1 and not args.no_gather
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2

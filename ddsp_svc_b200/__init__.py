@@ -5,8 +5,8 @@ API.  See DESIGN.md for the path, its boundary and the kernels; include/b200ddsp
 from . import _lib, ops, sharding, synthetic  # noqa: F401
 from .dropin import build_model, load_model, patch_reference, unpatch_reference  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
-from .sinegen import SineGen  # noqa: F401
+from .sinegen import SineGen, SourceModuleHnNSF  # noqa: F401
 from .vocoder import CombSub, CombSubSuperFast, FixedControls, Sins  # noqa: F401
 
-__all__ = ["Sins", "CombSub", "CombSubSuperFast", "SineGen", "FixedControls", "HostPipeline", "ops", "synthetic", "sharding",
+__all__ = ["Sins", "CombSub", "CombSubSuperFast", "SineGen", "SourceModuleHnNSF", "FixedControls", "HostPipeline", "ops", "synthetic", "sharding",
            "patch_reference", "unpatch_reference", "load_model", "build_model"]

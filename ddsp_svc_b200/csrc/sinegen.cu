@@ -68,6 +68,11 @@ struct SgParams {
     float thr;
     unsigned long long seed;
     long long utt_off;
+    // fused SourceModuleHnNSF tail (nsf_hifigan/models.py:201-204): merged[b,t] = tanh(lin_b + sum_h lin_w[h] out[b,t,h]);
+    // when `merged` is set the [B,T,dim] tensor is never written
+    const float* lin_w;     // [dim] or nullptr
+    float lin_b;
+    float* merged;          // [B, T] or nullptr
 };
 
 // sin(arg) for |arg| up to a few thousand rad: two-term Cody-Waite reduction, then the SFU.
@@ -143,15 +148,20 @@ __global__ void __launch_bounds__(kTile) sinegen_kernel(SgParams p) {
                 }
             }
         }
+        float lin = p.lin_b;
 #pragma unroll
         for (int h = 0; h < MAXD; ++h) {
             if (h < dim) {
                 const float theta = __fadd_rn(__fmul_rn(rad, (float)(h + 1)), __ldg(p.rand_ini + h));   // (:143,146)
                 const float sn = sin_reduced(__fmul_rn(B2D_TWO_PI_F, theta));                             // (:147)
-                row[h] = __fadd_rn(__fmul_rn(sn, samp_uv), __fmul_rn(namp, eps[h]));                      // (:159,163-164)
+                const float v = __fadd_rn(__fmul_rn(sn, samp_uv), __fmul_rn(namp, eps[h]));              // (:159,163-164)
+                if (p.merged) lin = fmaf(__ldg(p.lin_w + h), v, lin);                                     // l_linear (:203)
+                else row[h] = v;
             }
         }
+        if (p.merged) p.merged[(size_t)b * T + t] = tanhf(lin);                                           // l_tanh (:203)
     }
+    if (p.merged) return;          // uniform per launch: no tile to write back
     __syncthreads();
     float* dst = p.out + base;
     if ((base & 3) == 0 && (nflat & 3) == 0) {
@@ -162,18 +172,273 @@ __global__ void __launch_bounds__(kTile) sinegen_kernel(SgParams p) {
     }
 }
 
+
+// ---- v2: four consecutive samples per thread --------------------------------------------------------------
+// The kernel is issue-bound, not write-bound (ncu: 81 % issue-active at 23 % of DRAM peak), so v2 removes
+// instructions rather than bytes:
+//   * 4 samples x DIM harmonics = 4*DIM normals = exactly DIM Philox4x32-10 blocks (v1: ceil(DIM/4) blocks per
+//     sample, 12 normals for 9 harmonics); counter = flat quad index, so the stream is still a pure function of
+//     (seed, global utterance, position) and independent of how the batch is sharded;
+//   * Box-Muller straight on the .ftz approximate units (no denormal fix-up code around the MUFUs), uniforms
+//     assembled with integer ops, rint() by the add-magic-constant trick: the SFU pipe only sees 4 MUFU per
+//     normal pair and one per sine;
+//   * frame lookup, f0/sr, rand_ini and the Linear weights once per thread instead of once per sample;
+//   * PACKED: the reference-ordered fp32 chain of two samples at a time in f32x2 instructions
+//     (mul/add/fma.rn.f32x2 round each lane exactly like the scalar ops, so parity is unchanged);
+//   * FUSED (SourceModuleHnNSF): no shared-memory tile at all, one 128-bit store of 4 merged samples.
+constexpr int kQ = 4;
+constexpr int kThreads4 = 128;
+constexpr int kTile4 = kThreads4 * kQ;
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 dup2(float x) { return pack2(x, x); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_ftz(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_ftz(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Four standard normals from one Philox block (Box-Muller, two pairs).  The SFU ("XU") pipe is the scarce unit
+// here -- 16 lanes/clk/SM shared by MUFU, FRND and the int->float conversions -- so the uniforms are built with
+// integer ops (23 random mantissa bits under exponent 0: f in [1,2)) instead of I2F, and each pair costs exactly
+// four MUFU: LG2, SQRT, SIN, COS.
+//   radius: u = 2 - f in (0,1] (2^-23 granularity, |z| <= 5.65);  lg2(1) = +0 exactly, so a >= 0 and no clamp
+//   angle : sin/cos(2 pi f) = sin/cos(2 pi (f-1)): the whole turn is removed by the SFU's own range reduction
+__device__ __forceinline__ void normals4(const uint4 r, float* z) {
+    const float f1 = __uint_as_float((r.x >> 9) | 0x3f800000u), f2 = __uint_as_float((r.y >> 9) | 0x3f800000u);
+    const float f3 = __uint_as_float((r.z >> 9) | 0x3f800000u), f4 = __uint_as_float((r.w >> 9) | 0x3f800000u);
+    const float m1 = sqrt_ftz(lg2_ftz(2.0f - f1) * -1.3862943611198906f);      // sqrt(-2 ln u)
+    const float m3 = sqrt_ftz(lg2_ftz(2.0f - f3) * -1.3862943611198906f);
+    const float t2 = f2 * B2D_TWO_PI_F, t4 = f4 * B2D_TWO_PI_F;
+    z[0] = m1 * cos_ftz(t2); z[1] = m1 * sin_ftz(t2);
+    z[2] = m3 * cos_ftz(t4); z[3] = m3 * sin_ftz(t4);
+}
+
+// round to nearest integer (ties to even) on the FMA pipe instead of FRND (SFU): valid for |x| < 2^22
+#define B2D_RINT_MAGIC 12582912.0f
+__device__ __forceinline__ float rint_fma(float x) { return __fsub_rn(__fadd_rn(x, B2D_RINT_MAGIC), B2D_RINT_MAGIC); }
+
+// sin(fl(2 pi theta)) for theta (revolutions) up to a few hundred: k = rint(theta) is the multiple of 2 pi to remove
+__device__ __forceinline__ float sin_turns(float theta) {
+    const float arg = __fmul_rn(B2D_TWO_PI_F, theta);                                  // (:147) the reference's fp32 argument
+    const float k = rint_fma(theta);
+    float r = fmaf(k, -6.2831854820251465f, arg);
+    r = fmaf(k, 1.7484555e-7f, r);
+    return __sinf(r);
+}
+
+// MODE 0: scalar arithmetic; MODE 1: packed f32x2 arithmetic (default).  80 registers, 6 CTAs per SM.
+// Measured dead ends (B200, 64 x 10 s x 9): compiling for 8 CTAs/SM (64 registers) 0.357 vs 0.345 ms -- the
+// kernel is bound by the issue slots / pipe mix, not by latency; a streaming variant (one Philox block -> 4
+// outputs -> one 128-bit shared store, 48 registers) 0.42 ms, 320 M vs 248 M warp instructions.
+template <int DIM, bool FUSED, int MODE>
+__global__ void __launch_bounds__(kThreads4, 6) sinegen4_kernel(SgParams p) {
+    extern __shared__ __align__(16) float tile[];  // [kTile4 * DIM]; untouched when FUSED without noise_in
+    const int b = blockIdx.y;
+    const int T = p.nF * p.upp;
+    const int t0 = blockIdx.x * kTile4;
+    const int nt = min(kTile4, T - t0);
+    const int tid = threadIdx.x;
+    const size_t base = ((size_t)b * T + t0) * DIM;
+    const int nflat = nt * DIM;
+    const bool vec_ok = (base & 3) == 0 && (nflat & 3) == 0;
+
+    if (p.noise_in) {  // stage the noise tile (coalesced)
+        const float* src = p.noise_in + base;
+        if (vec_ok) {
+            for (int i = tid; i < (nflat >> 2); i += kThreads4)
+                reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        } else {
+            for (int i = tid; i < nflat; i += kThreads4) tile[i] = src[i];
+        }
+        __syncthreads();
+    }
+
+    const int lt = kQ * tid;                        // first local sample of this thread
+    float4* rows4 = reinterpret_cast<float4*>(tile + (size_t)lt * DIM);   // kQ*DIM floats = DIM float4, 16-byte aligned
+    if (lt < nt) {
+        const int tb = t0 + lt;
+        const unsigned long long utt = (unsigned long long)(p.utt_off + b);
+        const uint32_t q0 = (uint32_t)(tb >> 2) * DIM;          // flat quad index of this thread's first Philox block
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        float eps[kQ * DIM];                        // noise, then overwritten in place by the outputs
+        if (p.noise_in) {
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                const float4 v = rows4[c];
+                eps[4 * c] = v.x; eps[4 * c + 1] = v.y; eps[4 * c + 2] = v.z; eps[4 * c + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < DIM; ++c)
+                normals4(b2d::philox4x32_10(make_uint4(q0 + c, 0x51e6e004u, (uint32_t)utt, (uint32_t)(utt >> 32)), key), eps + 4 * c);
+        }
+        // per-sample frame quantities; consecutive samples share a frame except at a boundary
+        int k, j;
+        if (p.upp_shift >= 0) { k = tb >> p.upp_shift; j = tb & (p.upp - 1); }
+        else { k = tb / p.upp; j = tb - k * p.upp; }
+        float s, accp, namp, samp;
+        auto load_frame = [&](int kk) {
+            const float f = __ldg(p.f0 + (size_t)b * p.nF + kk);
+            s = __fdiv_rn(f, p.sr);                                                      // f0 / sr
+            accp = __ldg(p.acc_prev + (size_t)b * p.nF + kk);
+            const bool voiced = f > p.thr;
+            namp = voiced ? p.namp_voiced : p.namp_unvoiced;                             // (:162)
+            samp = voiced ? p.sine_amp : 0.0f;      // (sin*sine_amp)*uv == sin*(sine_amp*uv) for uv in {0,1}
+        };
+        load_frame(k);
+        float radv[kQ], nampv[kQ], sampv[kQ];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+            if (i > 0 && ++j == p.upp) { j = 0; ++k; if (k < p.nF) load_frame(k); }
+            radv[i] = __fadd_rn(__fmul_rn(s, (float)(j + 1)), accp);                    // (:138,141)
+            nampv[i] = namp; sampv[i] = samp;
+        }
+        float lin[kQ];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) lin[i] = p.lin_b;
+
+        if (MODE == 1) {
+            u64 rad2[kQ / 2], namp2[kQ / 2], samp2[kQ / 2];
+#pragma unroll
+            for (int g = 0; g < kQ / 2; ++g) {
+                rad2[g] = pack2(radv[2 * g], radv[2 * g + 1]);
+                namp2[g] = pack2(nampv[2 * g], nampv[2 * g + 1]);
+                samp2[g] = pack2(sampv[2 * g], sampv[2 * g + 1]);
+            }
+#pragma unroll
+            for (int h = 0; h < DIM; ++h) {
+                const float rho = __ldg(p.rand_ini + h);
+                const float wh = FUSED ? __ldg(p.lin_w + h) : 0.0f;
+#pragma unroll
+                for (int g = 0; g < kQ / 2; ++g) {
+                    const u64 th = add2(mul2(rad2[g], dup2((float)(h + 1))), dup2(rho));                 // (:143,146)
+                    const u64 arg = mul2(th, dup2(B2D_TWO_PI_F));                                           // (:147)
+                    const u64 kk = add2(add2(th, dup2(B2D_RINT_MAGIC)), dup2(-B2D_RINT_MAGIC));             // rint, FMA pipe
+                    float r0, r1;
+                    unpack2(fma2(kk, dup2(1.7484555e-7f), fma2(kk, dup2(-6.2831854820251465f), arg)), r0, r1);
+                    const u64 sn = pack2(__sinf(r0), __sinf(r1));
+                    const int e0 = (2 * g) * DIM + h, e1 = (2 * g + 1) * DIM + h;
+                    float v0, v1;
+                    unpack2(add2(mul2(sn, samp2[g]), mul2(namp2[g], pack2(eps[e0], eps[e1]))), v0, v1);  // (:159,163-164)
+                    if (FUSED) { lin[2 * g] = fmaf(wh, v0, lin[2 * g]); lin[2 * g + 1] = fmaf(wh, v1, lin[2 * g + 1]); }   // (:203)
+                    else { eps[e0] = v0; eps[e1] = v1; }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < DIM; ++h) {
+                const float rho = __ldg(p.rand_ini + h);
+                const float wh = FUSED ? __ldg(p.lin_w + h) : 0.0f;
+#pragma unroll
+                for (int i = 0; i < kQ; ++i) {
+                    const float theta = __fadd_rn(__fmul_rn(radv[i], (float)(h + 1)), rho);              // (:143,146)
+                    const float sn = sin_turns(theta);                                                       // (:147)
+                    const float v = __fadd_rn(__fmul_rn(sn, sampv[i]), __fmul_rn(nampv[i], eps[i * DIM + h]));   // (:159,163-164)
+                    if (FUSED) lin[i] = fmaf(wh, v, lin[i]);                                                 // (:203)
+                    else eps[i * DIM + h] = v;
+                }
+            }
+        }
+
+        if (FUSED) {
+            float* dst = p.merged + (size_t)b * T + tb;
+            if (tb + kQ <= T && ((((size_t)b * T + tb) & 3) == 0)) {
+                b2d::st_global_v4(dst, make_float4(tanhf(lin[0]), tanhf(lin[1]), tanhf(lin[2]), tanhf(lin[3])));   // l_tanh (:203)
+            } else {
+#pragma unroll
+                for (int i = 0; i < kQ; ++i) if (tb + i < T) dst[i] = tanhf(lin[i]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) rows4[c] = make_float4(eps[4 * c], eps[4 * c + 1], eps[4 * c + 2], eps[4 * c + 3]);
+        }
+    }
+    if (FUSED) return;
+    __syncthreads();
+    float* dst = p.out + base;
+    if (vec_ok) {
+        for (int i = tid; i < (nflat >> 2); i += kThreads4)
+            b2d::st_global_v4(dst + 4 * i, reinterpret_cast<const float4*>(tile)[i]);
+    } else {
+        for (int i = tid; i < nflat; i += kThreads4) dst[i] = tile[i];
+    }
+}
+
+template <int DIM, bool FUSED, int MODE>
+void launch_v2_as(const SgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static bool carveout_set = false;            // 18 KB tiles x 6 resident CTAs: ask for the large shared-memory split
+    if (!carveout_set) {
+        cudaFuncSetAttribute(sinegen4_kernel<DIM, FUSED, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
+    sinegen4_kernel<DIM, FUSED, MODE><<<grid, kThreads4, smem, st>>>(p);
+}
+
+template <int DIM>
+void launch_v2(const SgParams& p, int B, long long T, int impl, cudaStream_t st) {
+    const dim3 grid((unsigned)((T + kTile4 - 1) / kTile4), B);
+    const bool fused = p.merged != nullptr;
+    const size_t smem = (!fused || p.noise_in) ? (size_t)kTile4 * DIM * sizeof(float) : 0;
+    if (fused) {
+        if (impl == 2) launch_v2_as<DIM, true, 0>(p, grid, smem, st);
+        else launch_v2_as<DIM, true, 1>(p, grid, smem, st);
+    } else {
+        if (impl == 2) launch_v2_as<DIM, false, 0>(p, grid, smem, st);
+        else launch_v2_as<DIM, false, 1>(p, grid, smem, st);
+    }
+}
+
+int g_sinegen_impl = 0;   // 0 auto, 1 v1 (one sample per thread), 2 v2 scalar, 3 v2 packed f32x2
+
 }  // namespace
+
+extern "C" int b2d_set_sinegen_impl(int impl) {
+    if (impl < 0 || impl > 3) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_sinegen_impl: %d not in 0..3", impl);
+    g_sinegen_impl = impl;
+    return 0;
+}
+
+static int sinegen_launch(const float* f0, const float* rand_ini, const float* noise_in, uint64_t seed,
+                          int64_t utterance_offset, int B, int n_frames, int upp, int dim, double sampling_rate,
+                          float sine_amp, float noise_std, float voiced_threshold, float* acc_workspace, float* out,
+                          const float* lin_w, float lin_b, float* merged, void* stream);
 
 extern "C" int b2d_sinegen(const float* f0, const float* rand_ini, const float* noise_in, uint64_t seed,
                            int64_t utterance_offset, int B, int n_frames, int upp, int dim,
                            double sampling_rate, float sine_amp, float noise_std, float voiced_threshold,
                            float* acc_workspace, float* out, void* stream) {
-    if (!f0 || !rand_ini || !acc_workspace || !out) return b2d::fail(B2D_ERR_NULL, "sinegen: null pointer");
+    if (!out) return b2d::fail(B2D_ERR_NULL, "sinegen: null pointer");
+    return sinegen_launch(f0, rand_ini, noise_in, seed, utterance_offset, B, n_frames, upp, dim, sampling_rate, sine_amp,
+                          noise_std, voiced_threshold, acc_workspace, out, nullptr, 0.f, nullptr, stream);
+}
+
+extern "C" int b2d_source_module(const float* f0, const float* rand_ini, const float* noise_in, uint64_t seed,
+                                 int64_t utterance_offset, int B, int n_frames, int upp, int dim,
+                                 double sampling_rate, float sine_amp, float noise_std, float voiced_threshold,
+                                 const float* linear_weight, float linear_bias, float* acc_workspace, float* merged,
+                                 void* stream) {
+    if (!linear_weight || !merged) return b2d::fail(B2D_ERR_NULL, "source_module: null pointer");
+    return sinegen_launch(f0, rand_ini, noise_in, seed, utterance_offset, B, n_frames, upp, dim, sampling_rate, sine_amp,
+                          noise_std, voiced_threshold, acc_workspace, nullptr, linear_weight, linear_bias, merged, stream);
+}
+
+static int sinegen_launch(const float* f0, const float* rand_ini, const float* noise_in, uint64_t seed,
+                          int64_t utterance_offset, int B, int n_frames, int upp, int dim, double sampling_rate,
+                          float sine_amp, float noise_std, float voiced_threshold, float* acc_workspace, float* out,
+                          const float* lin_w, float lin_b, float* merged, void* stream) {
+    if (!f0 || !rand_ini || !acc_workspace) return b2d::fail(B2D_ERR_NULL, "sinegen: null pointer");
     if (B <= 0 || n_frames <= 0 || upp <= 0 || dim <= 0) return b2d::fail(B2D_ERR_SHAPE, "sinegen: bad shape");
     if (dim > kMaxDim) return b2d::fail(B2D_ERR_UNSUPPORTED, "sinegen: dim %d > %d", dim, kMaxDim);
     if (B > 65535) return b2d::fail(B2D_ERR_UNSUPPORTED, "sinegen: batch %d > 65535", B);
-    if (!b2d::aligned16(out) || (noise_in && !b2d::aligned16(noise_in)))
-        return b2d::fail(B2D_ERR_ALIGN, "sinegen: out / noise_in must be 16-byte aligned");
+    if ((out && !b2d::aligned16(out)) || (noise_in && !b2d::aligned16(noise_in)) || (merged && !b2d::aligned16(merged)))
+        return b2d::fail(B2D_ERR_ALIGN, "sinegen: out / merged / noise_in must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     sinegen_scan_kernel<<<B, kScanThreads, 0, st>>>(f0, n_frames, upp, (float)sampling_rate, acc_workspace);
     int rc = b2d::check_launch("sinegen_scan");
@@ -188,7 +453,14 @@ extern "C" int b2d_sinegen(const float* f0, const float* rand_ini, const float* 
     p.namp_voiced = (1.0f * noise_std) + ((0.0f * sine_amp) / 3.0f);
     p.namp_unvoiced = (0.0f * noise_std) + ((1.0f * sine_amp) / 3.0f);
     p.seed = seed; p.utt_off = utterance_offset;
+    p.lin_w = lin_w; p.lin_b = lin_b; p.merged = merged;
     const long long T = (long long)n_frames * upp;
+    const int impl = g_sinegen_impl == 0 ? 3 : g_sinegen_impl;
+    if (impl >= 2 && (dim == 9 || dim == 1)) {
+        if (dim == 9) launch_v2<9>(p, B, T, impl, st);
+        else launch_v2<1>(p, B, T, impl, st);
+        return b2d::check_launch("sinegen(v2)");
+    }
     const dim3 grid((unsigned)((T + kTile - 1) / kTile), B);
     const size_t smem = kTile * dim * sizeof(float);
     if (dim == 9) sinegen_kernel<9><<<grid, kTile, smem, st>>>(p);

@@ -78,7 +78,9 @@ def patch_reference():
     try:
         import nsf_hifigan.models as ref_nsf
         saved["SineGen"] = ref_nsf.SineGen
+        saved["SourceModuleHnNSF"] = ref_nsf.SourceModuleHnNSF
         ref_nsf.SineGen = sinegen.SineGen
+        ref_nsf.SourceModuleHnNSF = sinegen.SourceModuleHnNSF
     except Exception:                           # enhancer stack not importable: synthesizers only
         pass
     return saved
@@ -92,3 +94,5 @@ def unpatch_reference(saved):
     if "SineGen" in saved:
         import nsf_hifigan.models as ref_nsf
         ref_nsf.SineGen = saved["SineGen"]
+        if "SourceModuleHnNSF" in saved:
+            ref_nsf.SourceModuleHnNSF = saved["SourceModuleHnNSF"]

@@ -323,3 +323,35 @@ def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None
     _lib.check(rc, "b2d_superfast_synth")
     _count(1)
     return signal
+
+
+def source_module(f0, upp, sampling_rate, dim, rand_ini, linear_weight, linear_bias, sine_amp=0.1, noise_std=0.003,
+                  voiced_threshold=0.0, noise_in=None, seed=0, utterance_offset=0):
+    """SineGen + tanh(Linear(dim -> 1)) fused: f0 [B, nF] -> [B, nF*upp, 1]  (nsf_hifigan/models.py:201-204)."""
+    _need_cuda_f32("f0", f0)
+    f0 = f0.contiguous()
+    B, nF = f0.shape
+    rand_ini = rand_ini.to(device=f0.device, dtype=torch.float32).reshape(-1).contiguous()
+    w = linear_weight.detach().to(device=f0.device, dtype=torch.float32).reshape(-1).contiguous()
+    if rand_ini.numel() != dim or w.numel() != dim:
+        raise ValueError("rand_ini and linear_weight must have %d elements" % dim)
+    if noise_in is not None:
+        _need_cuda_f32("noise_in", noise_in)
+        if tuple(noise_in.shape) != (B, nF * upp, dim):
+            raise ValueError("noise_in must be [B, n_frames*upp, dim]")
+        noise_in = noise_in.contiguous()
+    out = torch.empty(B, nF * upp, 1, dtype=torch.float32, device=f0.device)
+    ws = torch.empty(B, nF, dtype=torch.float32, device=f0.device)
+    rc = _lib.lib().b2d_source_module(f0.data_ptr(), rand_ini.data_ptr(), _ptr(noise_in), int(seed), int(utterance_offset),
+                                      B, nF, int(upp), int(dim), float(sampling_rate), float(sine_amp), float(noise_std),
+                                      float(voiced_threshold), w.data_ptr(), float(linear_bias), ws.data_ptr(),
+                                      out.data_ptr(), _stream())
+    _lib.check(rc, "b2d_source_module")
+    _count(2)
+    return out
+
+
+def set_sinegen_impl(name):
+    """'auto' | 'v1' (one sample per thread) | 'v2' (four per thread) | 'v2p' (four per thread, packed f32x2)."""
+    impl = {"auto": 0, "v1": 1, "v2": 2, "v2p": 3}[name]
+    _lib.check(_lib.lib().b2d_set_sinegen_impl(impl), "b2d_set_sinegen_impl")

@@ -31,3 +31,30 @@ class SineGen(torch.nn.Module):
         return ops.sinegen(f0, int(upp), self.sampling_rate, self.dim, rand_ini, self.sine_amp, self.noise_std,
                            self.voiced_threshold, noise_in=noise, seed=0 if noise is not None else _host_seed(),
                            utterance_offset=utterance_offset)
+
+
+class SourceModuleHnNSF(torch.nn.Module):
+    """Drop-in for nsf_hifigan.models.SourceModuleHnNSF (models.py:168-204): SineGen followed by
+    tanh(Linear(harmonic_num+1 -> 1)), executed as ONE kernel that never writes the [B, T, dim] sines.
+    Same constructor (including the reference's ``voiced_threshod`` spelling) and state-dict keys
+    (``l_linear.weight``, ``l_linear.bias``)."""
+
+    def __init__(self, sampling_rate, harmonic_num=0, sine_amp=0.1, add_noise_std=0.003, voiced_threshod=0):
+        super().__init__()
+        self.sine_amp = sine_amp
+        self.noise_std = add_noise_std
+        self.l_sin_gen = SineGen(sampling_rate, harmonic_num, sine_amp, add_noise_std, voiced_threshod)
+        self.l_linear = torch.nn.Linear(harmonic_num + 1, 1)
+        self.l_tanh = torch.nn.Tanh()
+
+    def forward(self, x, upp, rand_ini=None, noise=None, utterance_offset=0):
+        g = self.l_sin_gen
+        if torch.is_grad_enabled() and self.l_linear.weight.requires_grad and self.training:
+            raise NotImplementedError("the fused source module is forward-only; use it under torch.no_grad()/eval()")
+        if rand_ini is None:
+            rand_ini = torch.rand(1, 1, g.dim, device=x.device)
+            rand_ini[..., 0] = 0
+        return ops.source_module(x, int(upp), g.sampling_rate, g.dim, rand_ini, self.l_linear.weight,
+                                 float(self.l_linear.bias.detach().reshape(-1)[0]), g.sine_amp, g.noise_std,
+                                 g.voiced_threshold, noise_in=noise, seed=0 if noise is not None else _host_seed(),
+                                 utterance_offset=utterance_offset)

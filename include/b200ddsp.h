@@ -205,6 +205,22 @@ int    b2d_superfast_synth(const void* workspace, const float* c_harmonic_magnit
                            uint64_t seed, int64_t utterance_offset, int B, int n_frames, int block,
                            int win_length, float* signal, void* stream);
 
+/* SineGen fused with the tail of SourceModuleHnNSF.   replaces nsf_hifigan/models.py:201-204
+ * (sine_merge = tanh(l_linear(sine_wavs))) on top of b2d_sinegen: merged [B, n_frames*upp] =
+ * tanh(linear_bias + sum_h linear_weight[h] * sine_wavs[..., h]); the [B, T, dim] tensor is never
+ * materialised (4 instead of 36 bytes per sample).  SURVEY 8(f) rank 2 ("next") fusion. */
+int b2d_source_module(const float* f0, const float* rand_ini, const float* noise_in, uint64_t seed,
+                      int64_t utterance_offset, int B, int n_frames, int upp, int dim,
+                      double sampling_rate, float sine_amp, float noise_std, float voiced_threshold,
+                      const float* linear_weight, float linear_bias, float* acc_workspace,
+                      float* merged, void* stream);
+
+/* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto, 1 one sample per
+ * thread (round-1 kernel; also the only one for dim other than 1 or 9), 2 four samples per thread,
+ * 3 four samples per thread with packed f32x2 arithmetic (auto).  Impl 1 and 2/3 draw DIFFERENT in-kernel
+ * noise streams (both Philox4x32-10 keyed by seed / global utterance / position). */
+int b2d_set_sinegen_impl(int impl);
+
 #ifdef __cplusplus
 }
 #endif

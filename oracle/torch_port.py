@@ -242,3 +242,12 @@ def sinegen_forward(f0, upp, sampling_rate, harmonic_num=8, sine_amp=0.1, noise_
     if noise is None:
         noise = torch.randn_like(sines)
     return {"rand_ini": rand_ini, "noise_in": noise, "out": sines * uv + noise_amp * noise}
+
+
+# ------------------------------------------------------------------------------------------
+# SourceModuleHnNSF tail                          (reference nsf_hifigan/models.py:201-204)
+# ------------------------------------------------------------------------------------------
+def source_module_forward(f0, upp, sampling_rate, weight, bias, harmonic_num=8, **kw):
+    """sine_merge = tanh(l_linear(sine_wavs)): [B, T, 1].  ``weight`` [1, dim], ``bias`` [1]."""
+    sines = sinegen_forward(f0, upp, sampling_rate, harmonic_num, **kw)["out"]          # (:202)
+    return {"out": torch.tanh(torch.nn.functional.linear(sines, weight, bias)), "sines": sines}   # (:203)

@@ -49,6 +49,9 @@ _add("superfast_b1_f2_constpad", kind="superfast", B=1, nF=2, win=2048, store=("
 # --- SineGen ----------------------------------------------------------------------------
 _add("sinegen_b2_f12", kind="sinegen", B=2, nF=12, upp=512, harmonic_num=8, unvoiced=0.25, store=("out",))
 _add("sinegen_b1_f3_upp256", kind="sinegen", B=1, nF=3, upp=256, harmonic_num=8, store=("out",))
+# SourceModuleHnNSF = SineGen + tanh(Linear(9 -> 1)); the golden also stores the seeded Linear parameters
+_add("srcmod_b2_f10", kind="source_module", B=2, nF=10, upp=512, harmonic_num=8, unvoiced=0.3,
+     store=("out",), extra=("weight", "bias"))
 
 
 def path(name):
@@ -77,7 +80,7 @@ def build_inputs(name):
     sd = seeds(name)
     B, nF = case["B"], case["nF"]
     out = {"case": case}
-    if case["kind"] == "sinegen":
+    if case["kind"] in ("sinegen", "source_module"):
         upp = case["upp"]
         out["f0"] = syn.make_f0(B, nF, SR, upp, seed=sd["f0"],
                                 unvoiced_fraction=case.get("unvoiced", 0.0))[..., 0].contiguous()

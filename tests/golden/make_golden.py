@@ -38,6 +38,14 @@ def run_reference(name):
             gen = SineGen(G.SR, harmonic_num=case["harmonic_num"])
             torch.manual_seed(sd["noise"])
             out["out"] = gen(inp["f0"], case["upp"])
+        elif case["kind"] == "source_module":
+            import nsf_hifigan.models as ref_nsf
+            torch.manual_seed(sd["ctrl"])                       # seeds the Linear(9 -> 1) initialisation
+            m = ref_nsf.SourceModuleHnNSF(G.SR, harmonic_num=case["harmonic_num"])
+            torch.manual_seed(sd["noise"])
+            out["out"] = m(inp["f0"], case["upp"])
+            out["weight"] = m.l_linear.weight.detach().clone()
+            out["bias"] = m.l_linear.bias.detach().clone()
         else:
             if case["kind"] == "sins":
                 m = V.Sins(G.SR, G.P, case["H"], case["Ma"], case["Mn"], n_unit=8)
@@ -68,7 +76,7 @@ def main():
         raise SystemExit("live reference not found; goldens can only be regenerated in the build container")
     for name, case in G.CASES.items():
         inp, out = run_reference(name)
-        payload = {k: out[k].numpy().astype(np.float32) for k in case["store"]}
+        payload = {k: out[k].numpy().astype(np.float32) for k in tuple(case["store"]) + tuple(case.get("extra", ()))}
         payload.update({k: np.float64(v) for k, v in G.input_checksums(inp).items()})
         payload["torch_version"] = np.array(torch.__version__)
         np.savez_compressed(G.path(name), **payload)

@@ -26,6 +26,10 @@ def test_buffers_and_forward_signature_without_reference():
     assert set(c.state_dict()) == {"sampling_rate", "block_size"}
     g = pkg.SineGen(44100, harmonic_num=8)
     assert g.dim == 9 and len(g.state_dict()) == 0
+    sm = pkg.SourceModuleHnNSF(44100, harmonic_num=8)
+    assert list(sm.state_dict()) == ["l_linear.weight", "l_linear.bias"]
+    assert sm.l_linear.weight.shape == (1, 9) and sm.l_sin_gen.dim == 9
+    assert "voiced_threshod" in inspect.signature(pkg.SourceModuleHnNSF.__init__).parameters   # reference spelling
     with pytest.raises(ValueError, match="Unknown Model"):
         dropin.build_model(dropin.DotDict({"model": {"type": "Nope"}, "data": {}}))
     with pytest.raises(RuntimeError, match="unit2ctrl"):
@@ -69,9 +73,13 @@ def test_state_dict_round_trip_with_the_reference_classes(tmp_path):
         try:
             assert V.Sins is pkg.Sins and V.CombSubSuperFast is pkg.CombSubSuperFast
             import nsf_hifigan.models as nsf
-            assert nsf.SineGen is pkg.SineGen
+            assert nsf.SineGen is pkg.SineGen and nsf.SourceModuleHnNSF is pkg.SourceModuleHnNSF
             model2, _ = V.load_model(str(tmp_path / "model_1.pt"), device="cpu")   # the REFERENCE's loader
             assert isinstance(model2, pkg.CombSubSuperFast)
         finally:
             pkg.unpatch_reference(saved)
-        assert V.Sins is not pkg.Sins
+        assert V.Sins is not pkg.Sins and nsf.SourceModuleHnNSF is not pkg.SourceModuleHnNSF
+        ref_sm = nsf.SourceModuleHnNSF(44100, harmonic_num=8)          # state dict of the reference class loads strictly
+        ours_sm = pkg.SourceModuleHnNSF(44100, harmonic_num=8)
+        assert list(ours_sm.state_dict()) == list(ref_sm.state_dict())
+        ours_sm.load_state_dict(ref_sm.state_dict())

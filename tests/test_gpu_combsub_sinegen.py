@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from ddsp_svc_b200 import CombSub, FixedControls, SineGen, ops, synthetic as syn
+from ddsp_svc_b200 import CombSub, FixedControls, SineGen, SourceModuleHnNSF, ops, synthetic as syn
 from tests import report, util
 from tests.golden import cases as G
 
@@ -132,3 +132,93 @@ def test_sinegen_full_size_config5():
     e = util.rms(got - ref)
     report.record("sinegen_full", row_rms=e, row_max=(got - ref).abs().max().item())
     assert e < GATE_RMS
+
+
+# ---- SourceModuleHnNSF: SineGen + tanh(Linear(9 -> 1)) in one kernel (nsf_hifigan/models.py:168-204) ----
+@pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "source_module"])
+def test_source_module_matches_reference_golden(name):
+    inp = G.build_inputs(name)
+    gold = util.load_golden(name)
+    case = inp["case"]
+    m = SourceModuleHnNSF(SR, harmonic_num=case["harmonic_num"])
+    m.load_state_dict({"l_linear.weight": torch.from_numpy(gold["weight"]), "l_linear.bias": torch.from_numpy(gold["bias"])})
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        out = m(inp["f0"].to(DEV), case["upp"], rand_ini=inp["rand_ini"].to(DEV), noise=inp["noise"].to(DEV)).cpu().numpy()
+    assert out.shape == gold["out"].shape == (case["B"], case["nF"] * case["upp"], 1)
+    e, mx = util.rms(out - gold["out"]), np.abs(out - gold["out"]).max()
+    report.record("source_module/" + name, rms=e, max=mx, ref_rms=util.rms(gold["out"]))
+    assert e < OFFICIAL_RMS and e < GATE_RMS
+    assert mx < 2e-5
+
+
+def test_source_module_equals_linear_tanh_of_sinegen():
+    """the fused kernel against tanh(linear(.)) applied to the UNFUSED kernel's own output, in-kernel noise on:
+    same Philox stream in both, so the two agree to fp32 rounding of a 9-term dot product."""
+    B, nF, upp, dim = 3, 40, 512, 9
+    f0v = syn.make_f0(B, nF, SR, upp, seed=21, unvoiced_fraction=0.2)[..., 0].contiguous().to(DEV)
+    ri = torch.rand(dim); ri[0] = 0
+    g = torch.Generator().manual_seed(3)
+    w, b = torch.randn(1, dim, generator=g), 0.37
+    sines = ops.sinegen(f0v, upp, SR, dim, ri, seed=77, utterance_offset=5)
+    want = torch.tanh(torch.nn.functional.linear(sines.double(), w.double().to(DEV)) + b)
+    got = ops.source_module(f0v, upp, SR, dim, ri, w, b, seed=77, utterance_offset=5)
+    assert got.shape == (B, nF * upp, 1)
+    err = (got.double() - want).abs().max().item()
+    report.record("source_module_fused_vs_unfused", max=err)
+    assert err < 2e-6
+
+
+@pytest.mark.parametrize("impl", ["v1", "v2", "v2p"])
+@pytest.mark.parametrize("upp,nF", [(130, 5), (512, 7), (3, 9)])
+def test_sinegen_kernel_variants_match_oracle(impl, upp, nF):
+    """every kernel variant (one / four samples per thread, scalar / packed f32x2) against the oracle port on
+    explicit noise, including hop sizes that are not powers of two and T not a multiple of 4 (ragged last thread)."""
+    from oracle import torch_port as tp
+    B, dim = 2, 9
+    f0 = syn.make_f0(B, nF, SR, upp, seed=31, unvoiced_fraction=0.3)[..., 0].contiguous()
+    g = torch.Generator().manual_seed(8)
+    ri = torch.rand(dim, generator=g); ri[0] = 0
+    z = torch.randn(B, nF * upp, dim, generator=g)
+    w, bias = torch.randn(1, dim, generator=g) / 3, torch.tensor([0.1])
+    ref = tp.source_module_forward(f0, upp, SR, w, bias, dim - 1, rand_ini=ri.reshape(1, 1, -1), noise=z)
+    ops.set_sinegen_impl(impl)
+    try:
+        got = ops.sinegen(f0.to(DEV), upp, SR, dim, ri, noise_in=z.to(DEV)).cpu()
+        merged = ops.source_module(f0.to(DEV), upp, SR, dim, ri, w, float(bias), noise_in=z.to(DEV)).cpu()
+        # in-kernel noise: fused and unfused draw the same stream inside one variant
+        a = ops.sinegen(f0.to(DEV), upp, SR, dim, ri, seed=5)
+        bm = ops.source_module(f0.to(DEV), upp, SR, dim, ri, w, float(bias), seed=5)
+        want = torch.tanh(torch.nn.functional.linear(a.double(), w.double().to(DEV)) + float(bias))
+    finally:
+        ops.set_sinegen_impl("auto")
+    e_sines = (got - ref["sines"]).abs().max().item()
+    e_merged = (merged - ref["out"]).abs().max().item()
+    report.record("sinegen_variant/%s/upp%d" % (impl, upp), max=e_sines, fused_max=e_merged)
+    assert got.shape == ref["sines"].shape and merged.shape == ref["out"].shape
+    assert e_sines < 2e-5 and util.rms((got - ref["sines"]).numpy()) < 1e-6
+    assert e_merged < 2e-5
+    assert (bm.double() - want).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("impl", ["v1", "v2p"])
+def test_sinegen_in_kernel_noise_moments_per_variant(impl):
+    B, nF, upp, dim = 4, 64, 512, 9
+    f0 = torch.zeros(B, nF, device=DEV)            # unvoiced: out = (sine_amp/3) * eps, so eps is observable
+    ri = torch.zeros(dim)
+    ops.set_sinegen_impl(impl)
+    try:
+        eps = (ops.sinegen(f0, upp, SR, dim, ri, seed=11) / (0.1 / 3)).double().cpu()
+    finally:
+        ops.set_sinegen_impl("auto")
+    n = eps.numel()
+    mean, var = eps.mean().item(), eps.var().item()
+    kurt = ((eps - mean) ** 4).mean().item() / var ** 2
+    assert abs(mean) < 5 / n ** 0.5 and abs(var - 1) < 0.01 and abs(kurt - 3) < 0.03
+    # no correlation between harmonics or between neighbouring samples
+    flat = eps.reshape(-1, dim)
+    c = torch.corrcoef(flat.T)
+    assert (c - torch.eye(dim)).abs().max().item() < 0.01
+    assert abs(torch.corrcoef(torch.stack([flat[:-1, 0], flat[1:, 0]]))[0, 1].item()) < 0.01
+    assert eps.abs().max().item() > 4.0            # tails present (24-bit radius)
+    report.record("sinegen_noise/" + impl, mean=mean, var=var, kurt=kurt)

@@ -36,6 +36,11 @@ def port_outputs(name, inp):
             return tp.combsub_forward(inp["f0"], inp["ctrls"], G.SR, G.P, noise=inp["noise"])
         if case["kind"] == "superfast":
             return tp.superfast_forward(inp["f0"], inp["ctrls"], G.SR, G.P, case["win"], noise=inp["noise"])
+        if case["kind"] == "source_module":
+            gold = load_golden(name)          # the seeded Linear(9 -> 1) parameters travel with the golden
+            return tp.source_module_forward(inp["f0"], case["upp"], G.SR, torch.from_numpy(gold["weight"]),
+                                            torch.from_numpy(gold["bias"]), case["harmonic_num"],
+                                            rand_ini=inp["rand_ini"], noise=inp["noise"])
         return tp.sinegen_forward(inp["f0"], case["upp"], G.SR, case["harmonic_num"],
                                   rand_ini=inp["rand_ini"], noise=inp["noise"])
 
@@ -52,5 +57,8 @@ def closed_form_outputs(name, inp):
         return cf.combsub(inp["f0"].numpy(), npc(inp["ctrls"]), G.SR, G.P, inp["noise"].numpy())
     if case["kind"] == "superfast":
         return cf.superfast(inp["f0"].numpy(), npc(inp["ctrls"]), G.SR, G.P, case["win"], inp["noise"].numpy())
-    return {"out": cf.sinegen(inp["f0"].numpy(), case["upp"], G.SR, inp["rand_ini"].numpy().reshape(-1),
-                              inp["noise"].numpy())}
+    sines = cf.sinegen(inp["f0"].numpy(), case["upp"], G.SR, inp["rand_ini"].numpy().reshape(-1), inp["noise"].numpy())
+    if case["kind"] == "source_module":
+        gold = load_golden(name)
+        return {"out": np.tanh(sines @ gold["weight"].astype(np.float64).T + gold["bias"].astype(np.float64))}
+    return {"out": sines}
