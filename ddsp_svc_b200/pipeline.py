@@ -6,14 +6,43 @@ memory (the reference's main.py does: main.py:201-215 copies in, :272 copies out
 the copies unless they overlap.  ``HostPipeline`` splits the batch into chunks of utterances
 (independent end to end) and overlaps the upload of chunk c+1, the kernels of chunk c and the
 download of chunk c-1.  PCIe is full duplex, so the steady state costs max(H2D, kernels, D2H).
+
+What is left outside the steady state is the upload of the FIRST chunk (nothing to compute yet) and the download
+of the LAST one (nothing left to compute), while every extra chunk costs ~0.1 ms of partially filled kernel
+waves.  ``chunks`` may therefore be a list of relative chunk sizes: a tapered schedule (small first and last
+chunk, large middle ones, e.g. ``(4, 9, 13, 6)``) shortens fill and drain without adding launches.
 """
 import torch
+
+
+def chunk_bounds(batch, chunks):
+    """[(lo, hi)] covering range(batch): ``chunks`` = number of (nearly) equal chunks, or a sequence of relative
+    sizes (largest-remainder rounding; empty chunks are dropped)."""
+    if isinstance(chunks, int):
+        n = max(1, min(chunks, batch))
+        base, rem = divmod(batch, n)
+        sizes = [base + (1 if c < rem else 0) for c in range(n)]
+    else:
+        w = [float(x) for x in chunks]
+        if not w or min(w) < 0 or sum(w) <= 0:
+            raise ValueError("chunk weights must be non-negative and not all zero")
+        exact = [x * batch / sum(w) for x in w]
+        sizes = [int(e) for e in exact]
+        for i in sorted(range(len(w)), key=lambda i: exact[i] - sizes[i], reverse=True)[:batch - sum(sizes)]:
+            sizes[i] += 1
+    bounds, lo = [], 0
+    for n in sizes:
+        if n > 0:
+            bounds.append((lo, lo + n))
+            lo += n
+    assert lo == batch
+    return bounds
 
 
 class HostPipeline:
     def __init__(self, device, chunks=4):
         self.device = torch.device(device)
-        self.chunks = int(chunks)
+        self.chunks = int(chunks) if isinstance(chunks, int) else tuple(chunks)
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
         self._dev = {}
@@ -38,13 +67,7 @@ class HostPipeline:
         B = out_host.shape[0]
         main = torch.cuda.current_stream(self.device)
         dev = {k: self._device_like(k, v) for k, v in host_inputs.items()}
-        n = max(1, min(self.chunks, B))
-        base, rem = divmod(B, n)
-        bounds, lo = [], 0
-        for c in range(n):
-            hi = lo + base + (1 if c < rem else 0)
-            bounds.append((lo, hi))
-            lo = hi
+        bounds = chunk_bounds(B, self.chunks)
         self.h2d.wait_stream(main)          # device buffers may still be in use by earlier work on `main`
         self.d2h.wait_stream(main)
         up = []

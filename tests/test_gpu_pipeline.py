@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("B,chunks", [(8, 3), (5, 4), (2, 8), (6, 1)])
+@pytest.mark.parametrize("B,chunks", [(8, 3), (5, 4), (2, 8), (6, 1), (8, (1, 3, 3, 1)), (5, (4, 9, 13, 6))])
 def test_host_pipeline_matches_direct_call(B, chunks):
     nF, H = 30, 64
     sm = syn.sins_split_map(H, 256, 256)

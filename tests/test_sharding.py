@@ -101,3 +101,22 @@ def test_synthesize_and_gather_pipeline_gloo(world, n_local, chunks):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get() is True
+
+
+def test_host_pipeline_chunk_bounds():
+    """even and tapered utterance chunk schedules of the host-buffer pipeline cover the batch exactly once"""
+    from ddsp_svc_b200.pipeline import chunk_bounds
+    assert chunk_bounds(32, 4) == [(0, 8), (8, 16), (16, 24), (24, 32)]
+    assert chunk_bounds(5, 4) == [(0, 2), (2, 3), (3, 4), (4, 5)]
+    assert chunk_bounds(2, 8) == [(0, 1), (1, 2)]
+    assert chunk_bounds(32, (4, 9, 13, 6)) == [(0, 4), (4, 13), (13, 26), (26, 32)]
+    for batch in (1, 2, 3, 7, 32, 33, 64):
+        for sched in ((4, 9, 13, 6), (1, 1), (4, 8, 12, 6, 2), (0, 1, 0)):
+            b = chunk_bounds(batch, sched)
+            assert b[0][0] == 0 and b[-1][1] == batch
+            assert all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(hi > lo for lo, hi in b)
+    sizes = [hi - lo for lo, hi in chunk_bounds(64, (4, 9, 13, 6))]
+    assert sizes == [8, 18, 26, 12]
+    import pytest
+    with pytest.raises(ValueError):
+        chunk_bounds(4, (0, 0))
