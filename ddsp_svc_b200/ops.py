@@ -45,11 +45,16 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _need_cuda_f32(name, t, dtype=torch.float32):
+def _need_cuda_f32(name, t, dtype=torch.float32, local=True):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise ValueError("%s must be a CUDA tensor (the B200 kernels have no CPU fallback)" % name)
     if t.dtype != dtype:
         raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if local and t.device.index != torch.cuda.current_device():
+        # the library launches on the calling thread's current device and on torch's current stream of it
+        raise ValueError("%s lives on %s but the current CUDA device is %d; call torch.cuda.set_device(%d) "
+                         "(one process per GPU) or wrap the call in torch.cuda.device(...)"
+                         % (name, t.device, torch.cuda.current_device(), t.device.index))
 
 
 def _frames_2d(f0_frames):
@@ -187,7 +192,7 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
     ws_bytes = L.b2d_sins_workspace_bytes(B, nF, int(block), Ma, Mn)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if signal_out is not None:
-        _need_cuda_f32("signal_out", signal_out)
+        _need_cuda_f32("signal_out", signal_out, local=False)        # may be peer-mapped memory of another GPU
         if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
             raise ValueError("signal_out must be a contiguous [B, T] tensor")
         signal = signal_out
@@ -271,7 +276,7 @@ def combsub_synth(f0_frames, frame_phase, c_group_delay, c_harmonic, c_noise, bl
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     signal, harmonic, noise = (torch.empty(B, T, dtype=torch.float32, device=dev) for _ in range(3))
     if signal_out is not None:
-        _need_cuda_f32("signal_out", signal_out)
+        _need_cuda_f32("signal_out", signal_out, local=False)        # may be peer-mapped memory of another GPU
         if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
             raise ValueError("signal_out must be a contiguous [B, T] tensor")
         signal = signal_out
@@ -311,7 +316,7 @@ def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None
         _need_cuda_f32("noise_in", noise_in)
         noise_in = noise_in.reshape(B, T).contiguous()
     if signal_out is not None:
-        _need_cuda_f32("signal_out", signal_out)
+        _need_cuda_f32("signal_out", signal_out, local=False)        # may be peer-mapped memory of another GPU
         if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
             raise ValueError("signal_out must be a contiguous [B, T] tensor")
         signal = signal_out

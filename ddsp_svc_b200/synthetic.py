@@ -88,6 +88,12 @@ def superfast_split_map(win_length=2048):
                         ("noise_magnitude", n), ("noise_phase", n)])
 
 
+def combsubfast_split_map(block_size=512):
+    """CombSubFast predicts block_size+1 bins per control (reference ddsp/vocoder.py:728-732)."""
+    n = block_size + 1
+    return OrderedDict([("harmonic_magnitude", n), ("harmonic_phase", n), ("noise_magnitude", n)])
+
+
 def uniform_noise(batch, n_samples, seed):
     """What ``torch.rand_like(x) * 2 - 1`` yields in the reference (ddsp/vocoder.py:603)
     when ``torch.manual_seed(seed)`` was called just before forward()."""

@@ -151,6 +151,32 @@ def combsub(f0_frames, ctrls, sr, P, noise, initial_phase=None):
             "ir_noise": ir_n, "harmonic": harmonic, "noise": noise_out, "signal": harmonic + noise_out}
 
 
+def combsubfast(f0_frames, ctrls, sr, P, noise, initial_phase=None):
+    """(ddsp/vocoder.py:735-786) in float64: frames of 2P at hop P, sqrt-Hann in and out, filter of frame q =
+    control row min(q, nF-1), plain overlap-add, cropped by P on both sides."""
+    x = phase_cycles(f0_frames, sr, P, initial_phase)
+    x32 = x.astype(np.float32).astype(np.float64)           # the reference rounds x to fp32 (:751)
+    f0_up = upsample(f0_frames, P)[..., 0]
+    comb = np.sinc(sr * x32 / (f0_up + 1e-3))
+    B, T = comb.shape
+    nF = T // P
+    N = 2 * P
+    w = np.sqrt(0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N))
+    hm = np.asarray(ctrls["harmonic_magnitude"], np.float64)
+    hp = np.asarray(ctrls["harmonic_phase"], np.float64)
+    nm = np.asarray(ctrls["noise_magnitude"], np.float64)
+    h_src = _hold(np.exp(hm + 1j * np.pi * hp))
+    h_noise = _hold(np.exp(nm) / 128.0)
+    pad = lambda z: np.concatenate([np.zeros((B, P)), np.asarray(z, np.float64), np.zeros((B, P))], axis=1)
+    cp, zp = pad(comb), pad(noise)
+    out = np.zeros((B, T + 2 * P))
+    for q in range(nF + 1):
+        seg = slice(q * P, q * P + N)
+        spec = np.fft.rfft(cp[:, seg] * w, N) * h_src[:, q] + np.fft.rfft(zp[:, seg] * w, N) * h_noise[:, q]
+        out[:, seg] += np.fft.irfft(spec, N) * w
+    return {"x": x, "comb": comb, "signal": out[:, P:-P]}
+
+
 def superfast_phase(f0_frames, sr, P):
     """Wrapped in-frame phase of fast_source_gen in exact arithmetic (ddsp/vocoder.py:639-651)."""
     s = np.asarray(f0_frames, np.float64)[..., 0] / sr

@@ -218,6 +218,31 @@ def superfast_forward(f0_frames, ctrls, sampling_rate, block, win_length, noise=
 
 
 # --------------------------------------------------------------------------------------
+# CombSubFast                                    (reference ddsp/vocoder.py:735-786)
+# --------------------------------------------------------------------------------------
+def combsubfast_forward(f0_frames, ctrls, sampling_rate, block, noise=None, initial_phase=None, infer=True):
+    """sqrt-Hann analysis/synthesis frames of 2*block at hop block; per-frame complex source filter and real
+    noise filter applied in the rfft domain; plain overlap-add (sqrt-Hann^2 is COLA at 50 % overlap)."""
+    sr = torch.tensor(sampling_rate)
+    x, f0_up = wrapped_phase(f0_frames, sampling_rate, block, initial_phase, infer)       # (:743-751)
+    phase_frames = TWO_PI * x[:, ::block, :]                                              # (:753)
+    hold_last = lambda z: torch.cat((z, z[:, -1:, :]), dim=1)
+    h_src = hold_last(torch.exp(ctrls["harmonic_magnitude"] + 1.j * math.pi * ctrls["harmonic_phase"]))   # (:758-759)
+    h_noise = hold_last(torch.exp(ctrls["noise_magnitude"]) / 128)                        # (:760-761)
+    comb = torch.sinc(sr * x / (f0_up + 1e-3)).squeeze(-1)                                # (:764-765)
+    n_fft = 2 * block
+    window = torch.sqrt(torch.hann_window(n_fft))                                         # (:726)
+    frames_of = lambda z: F.pad(z, (block, block)).unfold(1, n_fft, block) * window       # (:766-767, :772-773)
+    if noise is None:
+        noise = torch.rand_like(comb) * 2 - 1                                             # (:771)
+    spec = torch.fft.rfft(frames_of(comb), n_fft) * h_src + torch.fft.rfft(frames_of(noise), n_fft) * h_noise   # (:768-777)
+    pieces = torch.fft.irfft(spec, n_fft) * window                                        # (:780)
+    ola = torch.nn.Fold(output_size=(1, (pieces.size(1) + 1) * block), kernel_size=(1, n_fft), stride=(1, block))
+    signal = ola(pieces.transpose(1, 2))[:, 0, 0, block:-block]                           # (:783-784)
+    return {"x": x, "phase_frames": phase_frames, "comb": comb, "noise_in": noise, "signal": signal}
+
+
+# --------------------------------------------------------------------------------------
 # SineGen                                        (reference nsf_hifigan/models.py:134-165)
 # --------------------------------------------------------------------------------------
 def sinegen_forward(f0, upp, sampling_rate, harmonic_num=8, sine_amp=0.1, noise_std=0.003,

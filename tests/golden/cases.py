@@ -46,6 +46,11 @@ _add("combsub_b1_f3_unvoiced", kind="combsub", B=1, nF=3, Ma=256, Mh=512, Mn=256
 _add("superfast_b2_f24", kind="superfast", B=2, nF=24, win=2048, store=("signal", "phase_frames"))
 _add("superfast_b1_f5", kind="superfast", B=1, nF=5, win=2048, store=("signal", "phase_frames"))
 _add("superfast_b1_f2_constpad", kind="superfast", B=1, nF=2, win=2048, store=("signal", "phase_frames"))
+# --- CombSubFast (1024-point sqrt-Hann frames; the variant the diffusion / reflow vocoders embed) --------
+_add("csfast_b2_f24", kind="combsubfast", B=2, nF=24, unvoiced=0.1, sweep_row=1, store=("signal", "phase_frames"))
+_add("csfast_b1_f3_unvoiced", kind="combsubfast", B=1, nF=3, unvoiced=0.4, store=("signal", "phase_frames"))
+_add("csfast_b1_f1", kind="combsubfast", B=1, nF=1, store=("signal", "phase_frames"))
+_add("csfast_b1_f9_initphase", kind="combsubfast", B=1, nF=9, initial_phase=True, store=("signal", "phase_frames"))
 # --- SineGen ----------------------------------------------------------------------------
 _add("sinegen_b2_f12", kind="sinegen", B=2, nF=12, upp=512, harmonic_num=8, unvoiced=0.25, store=("out",))
 _add("sinegen_b1_f3_upp256", kind="sinegen", B=1, nF=3, upp=256, harmonic_num=8, store=("out",))
@@ -66,6 +71,8 @@ def split_map(case):
         return syn.combsub_split_map(case["Ma"], case["Mh"], case["Mn"])
     if k == "superfast":
         return syn.superfast_split_map(case["win"])
+    if k == "combsubfast":
+        return syn.combsubfast_split_map(P)
     return None
 
 

@@ -51,6 +51,8 @@ def run_reference(name):
                 m = V.Sins(G.SR, G.P, case["H"], case["Ma"], case["Mn"], n_unit=8)
             elif case["kind"] == "combsub":
                 m = V.CombSub(G.SR, G.P, case["Ma"], case["Mh"], case["Mn"], n_unit=8)
+            elif case["kind"] == "combsubfast":
+                m = V.CombSubFast(G.SR, G.P, n_unit=8)
             else:
                 m = V.CombSubSuperFast(G.SR, G.P, case["win"], n_unit=8)
             m.eval()

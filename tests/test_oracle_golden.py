@@ -14,7 +14,7 @@ from tests import util
 
 # per-kind (rms, max) bound of |closed_form - reference|: the reference's own fp32 error
 CF_BOUNDS = {"sins": (2e-7, 2e-6), "combsub": (2e-7, 2e-6), "superfast": (5e-6, 2e-4),
-             "sinegen": (5e-6, 5e-5), "source_module": (5e-6, 5e-5)}
+             "sinegen": (5e-6, 5e-5), "source_module": (5e-6, 5e-5), "combsubfast": (5e-7, 5e-6)}
 
 
 @pytest.mark.parametrize("name", list(G.CASES))

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="live referen
 
 @pytest.mark.parametrize("name", ["sins_b2_f24_h128", "sins_b1_f7_h33", "sins_b1_f12_h40_m65_initphase",
                                   "combsub_b2_f24", "superfast_b2_f24", "superfast_b1_f2_constpad",
-                                  "sinegen_b2_f12"])
+                                  "sinegen_b2_f12", "csfast_b2_f24", "csfast_b1_f9_initphase", "srcmod_b2_f10"])
 def test_port_bit_identical_to_live_reference(name):
     with contextlib.redirect_stdout(io.StringIO()):
         inp, ref = make_golden.run_reference(name)

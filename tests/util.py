@@ -36,6 +36,9 @@ def port_outputs(name, inp):
             return tp.combsub_forward(inp["f0"], inp["ctrls"], G.SR, G.P, noise=inp["noise"])
         if case["kind"] == "superfast":
             return tp.superfast_forward(inp["f0"], inp["ctrls"], G.SR, G.P, case["win"], noise=inp["noise"])
+        if case["kind"] == "combsubfast":
+            return tp.combsubfast_forward(inp["f0"], inp["ctrls"], G.SR, G.P, noise=inp["noise"],
+                                          initial_phase=inp.get("initial_phase"))
         if case["kind"] == "source_module":
             gold = load_golden(name)          # the seeded Linear(9 -> 1) parameters travel with the golden
             return tp.source_module_forward(inp["f0"], case["upp"], G.SR, torch.from_numpy(gold["weight"]),
@@ -55,6 +58,10 @@ def closed_form_outputs(name, inp):
                        None if ip is None else ip.numpy())
     if case["kind"] == "combsub":
         return cf.combsub(inp["f0"].numpy(), npc(inp["ctrls"]), G.SR, G.P, inp["noise"].numpy())
+    if case["kind"] == "combsubfast":
+        ip = inp.get("initial_phase")
+        return cf.combsubfast(inp["f0"].numpy(), npc(inp["ctrls"]), G.SR, G.P, inp["noise"].numpy(),
+                              None if ip is None else ip.numpy())
     if case["kind"] == "superfast":
         return cf.superfast(inp["f0"].numpy(), npc(inp["ctrls"]), G.SR, G.P, case["win"], inp["noise"].numpy())
     sines = cf.sinegen(inp["f0"].numpy(), case["upp"], G.SR, inp["rand_ini"].numpy().reshape(-1), inp["noise"].numpy())
