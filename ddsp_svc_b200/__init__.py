@@ -6,7 +6,7 @@ from . import _lib, ops, sharding, synthetic  # noqa: F401
 from .dropin import build_model, load_model, patch_reference, unpatch_reference  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 from .sinegen import SineGen, SourceModuleHnNSF  # noqa: F401
-from .vocoder import CombSub, CombSubSuperFast, FixedControls, Sins  # noqa: F401
+from .vocoder import CombSub, CombSubFast, CombSubSuperFast, FixedControls, Sins  # noqa: F401
 
-__all__ = ["Sins", "CombSub", "CombSubSuperFast", "SineGen", "SourceModuleHnNSF", "FixedControls", "HostPipeline", "ops", "synthetic", "sharding",
+__all__ = ["Sins", "CombSub", "CombSubSuperFast", "CombSubFast", "SineGen", "SourceModuleHnNSF", "FixedControls", "HostPipeline", "ops", "synthetic", "sharding",
            "patch_reference", "unpatch_reference", "load_model", "build_model"]

@@ -40,6 +40,9 @@ _MODEL_TYPES = {
         sampling_rate=a.data.sampling_rate, block_size=a.data.block_size, n_mag_allpass=a.model.n_mag_allpass,
         n_mag_harmonic=a.model.n_mag_harmonic, n_mag_noise=a.model.n_mag_noise,
         n_unit=a.data.encoder_out_channels, n_spk=a.model.n_spk),
+    "CombSubFast": lambda a: vocoder.CombSubFast(            # experimental, see vocoder.CombSubFast
+        sampling_rate=a.data.sampling_rate, block_size=a.data.block_size,
+        n_unit=a.data.encoder_out_channels, n_spk=a.model.n_spk),
     "CombSubSuperFast": lambda a: vocoder.CombSubSuperFast(
         sampling_rate=a.data.sampling_rate, block_size=a.data.block_size, win_length=a.model.win_length,
         n_unit=a.data.encoder_out_channels, n_spk=a.model.n_spk),
@@ -67,14 +70,15 @@ def load_model(model_path, device="cuda"):
     return model, args
 
 
-def patch_reference():
+def patch_reference(experimental=False):
     """Swap the synthesizer classes inside the (importable) reference package.  Returns the dict
-    of original classes so a caller can restore them."""
+    of original classes so a caller can restore them.  ``experimental=True`` also swaps ``CombSubFast``,
+    whose kernel has not been validated on hardware yet."""
     import ddsp.vocoder as ref_vocoder          # the reference checkout must be on sys.path
-    saved = {name: getattr(ref_vocoder, name) for name in ("Sins", "CombSub", "CombSubSuperFast")}
-    ref_vocoder.Sins = vocoder.Sins
-    ref_vocoder.CombSub = vocoder.CombSub
-    ref_vocoder.CombSubSuperFast = vocoder.CombSubSuperFast
+    names = ("Sins", "CombSub", "CombSubSuperFast") + (("CombSubFast",) if experimental else ())
+    saved = {name: getattr(ref_vocoder, name) for name in names}
+    for name in names:
+        setattr(ref_vocoder, name, getattr(vocoder, name))
     try:
         import nsf_hifigan.models as ref_nsf
         saved["SineGen"] = ref_nsf.SineGen
@@ -88,7 +92,7 @@ def patch_reference():
 
 def unpatch_reference(saved):
     import ddsp.vocoder as ref_vocoder
-    for name in ("Sins", "CombSub", "CombSubSuperFast"):
+    for name in ("Sins", "CombSub", "CombSubSuperFast", "CombSubFast"):
         if name in saved:
             setattr(ref_vocoder, name, saved[name])
     if "SineGen" in saved:

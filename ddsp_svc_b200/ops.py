@@ -360,3 +360,26 @@ def set_sinegen_impl(name):
     """'auto' | 'v1' (one sample per thread) | 'v2' (four per thread) | 'v2p' (four per thread, packed f32x2)."""
     impl = {"auto": 0, "v1": 1, "v2": 2, "v2p": 3}[name]
     _lib.check(_lib.lib().b2d_set_sinegen_impl(impl), "b2d_set_sinegen_impl")
+
+
+def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utterance_offset=0):
+    """CombSubFast after the source: comb [B, T] + raw controls [B, nF, block+1] -> signal [B, T]
+    (reference ddsp/vocoder.py:758-784).  EXPERIMENTAL: not yet validated on hardware."""
+    _need_cuda_f32("comb", comb)
+    B, T = comb.shape
+    nF = T // block
+    (hm, hp, nm), stride = _same_stride([("harmonic_magnitude", c_hm), ("harmonic_phase", c_hp),
+                                         ("noise_magnitude", c_nm)], B, nF)
+    if hm.shape[2] != block + 1:
+        raise ValueError("controls must have block_size+1 = %d bins" % (block + 1))
+    comb = comb.contiguous()
+    if noise_in is not None:
+        _need_cuda_f32("noise_in", noise_in)
+        noise_in = noise_in.reshape(B, T).contiguous()
+    signal = torch.empty(B, T, dtype=torch.float32, device=comb.device)
+    rc = _lib.lib().b2d_combsubfast_filter(comb.data_ptr(), hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), stride,
+                                           _ptr(noise_in), int(seed), int(utterance_offset), B, nF, int(block),
+                                           signal.data_ptr(), _stream())
+    _lib.check(rc, "b2d_combsubfast_filter")
+    _count(1)
+    return signal

@@ -161,6 +161,43 @@ class CombSubSuperFast(_SynthBase):
         return signal, hidden, (signal, signal)
 
 
+class CombSubFast(_SynthBase):
+    """Combtooth subtractive synthesiser with 2*block sqrt-Hann frames (the variant the diffusion / reflow vocoders
+    embed) -- reference ddsp/vocoder.py:712-786.  Returns (signal, hidden, (signal, signal)) like the reference.
+
+    EXPERIMENTAL: the kernel (csrc/combsubfast.cu) is pinned by a CPU model of its algorithm and builds for
+    sm_100a, but has not been run on hardware yet; ``patch_reference()`` therefore leaves the reference class in
+    place unless ``experimental=True`` is passed."""
+
+    def __init__(self, sampling_rate, block_size, n_unit=256, n_spk=1, use_pitch_aug=False, pcmer_norm=False,
+                 unit2ctrl=None):
+        super().__init__()
+        self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
+        self.register_buffer("block_size", torch.tensor(block_size))
+        self.register_buffer("window", torch.sqrt(torch.hann_window(2 * block_size)))
+        split_map = {
+            "harmonic_magnitude": block_size + 1,
+            "harmonic_phase": block_size + 1,
+            "noise_magnitude": block_size + 1,
+        }
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _reference_unit2ctrl(
+            n_unit, n_spk, split_map, use_pitch_aug=use_pitch_aug, pcmer_norm=pcmer_norm)
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, aug_shift=None,
+                initial_phase=None, infer=True, noise=None, utterance_offset=0, **kwargs):
+        sr, block = self._scalars()
+        frame_phase, phase_frames = ops.phase_scan(f0_frames, block, sr, initial_phase, infer)
+        ctrls, hidden = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id=spk_id,
+                                       spk_mix_dict=spk_mix_dict, aug_shift=aug_shift)
+        self._forward_only(ctrls)
+        comb = ops.comb_source(f0_frames, frame_phase, block, sr, infer)
+        signal = ops.combsubfast_filter(comb, ctrls["harmonic_magnitude"], ctrls["harmonic_phase"],
+                                        ctrls["noise_magnitude"], block, noise_in=noise,
+                                        seed=0 if noise is not None else _host_seed(),
+                                        utterance_offset=utterance_offset)
+        return signal, hidden, (signal, signal)
+
+
 class FixedControls(torch.nn.Module):
     """Stand-in for Unit2Control that returns preset raw controls: isolates the DSP path (the
     seam the parity tests and the benchmark use; reference ddsp/vocoder.py:578)."""

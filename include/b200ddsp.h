@@ -215,6 +215,18 @@ int b2d_source_module(const float* f0, const float* rand_ini, const float* noise
                       const float* linear_weight, float linear_bias, float* acc_workspace,
                       float* merged, void* stream);
 
+/* CombSubFast STFT-domain filter.   replaces ddsp/vocoder.py:758-784
+ * comb [B, T] is the comb-tooth source of b2d_comb_source (the same expression as :764 on the same phase,
+ * :743-751 = b2d_phase_scan); controls are raw Unit2Control outputs [B, n_frames, block+1] with a common frame
+ * stride; noise_in [B, T] uniform(-1,1) or NULL = in-kernel Philox (same stream as b2d_ltv_fir).
+ * Frames of 2*block at hop block, sqrt-Hann analysis and synthesis windows, filter row min(q, n_frames-1),
+ * overlap-add cropped by block on both sides.  block must be 512.
+ * STATUS: built and pinned by a CPU model of the kernel (tests/test_csfast_math.py); not yet run on hardware. */
+int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude, const float* c_harmonic_phase,
+                           const float* c_noise_magnitude, int64_t ctrl_stride, const float* noise_in,
+                           uint64_t seed, int64_t utterance_offset, int B, int n_frames, int block,
+                           float* signal, void* stream);
+
 /* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto, 1 one sample per
  * thread (round-1 kernel; also the only one for dim other than 1 or 9), 2 four samples per thread,
  * 3 four samples per thread with packed f32x2 arithmetic (auto).  Impl 1 and 2/3 draw DIFFERENT in-kernel

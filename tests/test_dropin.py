@@ -24,6 +24,8 @@ def test_buffers_and_forward_signature_without_reference():
         assert name in sig.parameters
     c = pkg.CombSub(44100, 512, 256, 512, 256, unit2ctrl=pkg.FixedControls())
     assert set(c.state_dict()) == {"sampling_rate", "block_size"}
+    cf = pkg.CombSubFast(44100, 512, unit2ctrl=pkg.FixedControls())
+    assert list(cf.state_dict()) == ["sampling_rate", "block_size", "window"] and cf.window.shape == (1024,)
     g = pkg.SineGen(44100, harmonic_num=8)
     assert g.dim == 9 and len(g.state_dict()) == 0
     sm = pkg.SourceModuleHnNSF(44100, harmonic_num=8)
@@ -52,6 +54,7 @@ def test_state_dict_round_trip_with_the_reference_classes(tmp_path):
             (V.Sins(44100, 512, 128, 256, 256, n_unit=768, n_spk=1), lambda: pkg.Sins(44100, 512, 128, 256, 256, n_unit=768, n_spk=1)),
             (V.CombSub(44100, 512, 256, 512, 256, n_unit=768, n_spk=2), lambda: pkg.CombSub(44100, 512, 256, 512, 256, n_unit=768, n_spk=2)),
             (V.CombSubSuperFast(44100, 512, 2048, n_unit=768, n_spk=1), lambda: pkg.CombSubSuperFast(44100, 512, 2048, n_unit=768, n_spk=1)),
+            (V.CombSubFast(44100, 512, n_unit=768, n_spk=1), lambda: pkg.CombSubFast(44100, 512, n_unit=768, n_spk=1)),
         ]
         for ref_model, make in cases:
             ours = make()                                   # uses the reference's Unit2Control
@@ -72,6 +75,7 @@ def test_state_dict_round_trip_with_the_reference_classes(tmp_path):
         saved = pkg.patch_reference()
         try:
             assert V.Sins is pkg.Sins and V.CombSubSuperFast is pkg.CombSubSuperFast
+            assert V.CombSubFast is not pkg.CombSubFast            # experimental classes are opt-in
             import nsf_hifigan.models as nsf
             assert nsf.SineGen is pkg.SineGen and nsf.SourceModuleHnNSF is pkg.SourceModuleHnNSF
             model2, _ = V.load_model(str(tmp_path / "model_1.pt"), device="cpu")   # the REFERENCE's loader
