@@ -396,6 +396,8 @@ def main():
                     help="utterance chunks of the host-buffer pipeline: a count (1 = serial) or comma-separated "
                          "relative sizes (default tapered: short fill and drain; measured 2.57 ms vs 2.72 ms "
                          "for 4 equal chunks on the Sins workload)")
+    ap.add_argument("--fir-impl", default="auto", choices=["auto", "cuda", "tc", "cuda8", "fft"],
+                    help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
     ap.add_argument("--sinegen-impl", default="auto", choices=["auto", "v1", "v2", "v2p"],
                     help="A/B switch for the SineGen / source-module kernel (ops.set_sinegen_impl)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
@@ -424,6 +426,8 @@ def main():
     e2e_chunks = int(args.e2e_chunks) if args.e2e_chunks.isdigit() else tuple(int(x) for x in args.e2e_chunks.split(","))
     if args.sinegen_impl != "auto":
         run.ops.set_sinegen_impl(args.sinegen_impl)
+    if args.fir_impl != "auto":
+        run.ops.set_fir_impl(args.fir_impl)
     B, nF, T = run.B, run.nF, run.T
     do_gather = world > 1 and not args.no_gather
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2

@@ -7,7 +7,7 @@
 //     out   = overlap-add( w * irfft(S_q) ), cropped by P on both sides; no envelope division (w^2 is COLA)
 //
 // Design (B200).  HBM traffic: 3 x 513 control values per frame = 12 B per output sample, + 4 B comb in and 4 B
-// out; everything else stays on chip.
+// out; everything else stays on chip.  23.4 KB shared memory, 128 registers -> 4 CTAs per SM.
 //  * one CTA owns G consecutive hops of one utterance and walks the G+1 frames that touch them, TWO frames
 //    per iteration;
 //  * per frame one complex 1024-point FFT carries w*(comb + j*noise); both frames of the pair run as a batch
@@ -26,72 +26,13 @@
 #ifndef B2D_HOST_EMU               // tests/emu/ runs this kernel's source on the CPU (host_emu.h provides the shims)
 #include "b2d_common.cuh"
 #endif
-#include "fft_regs.cuh"
+#include "fft1024.cuh"
 
-using namespace b2d_fft;
+using namespace b2d_fft1024;
 
 namespace {
 
-constexpr int kP = 512, kN = 1024, kThreads = 128;
-constexpr int kPad = kN + kN / 16;      // complex slots of one padded FFT buffer
-constexpr int kTw2 = 7 * 16;            // exp(-2 pi i r k / 128), r = 1..7, k < 16
-constexpr int kTw3 = 128;               // exp(-2 pi i k / 1024), k < 128
-
-__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }   // one pad slot per 16: conflict-free passes
-
-// One radix-R Stockham pass over NBATCH independent 1024-point FFTs stored back to back (FFT g at buf + g*kPad),
-// in place (all reads, barrier, all writes, barrier).
-//   butterfly j: v[r] = in[j + r N/R] * exp(-2 pi i r (j % NS) / (NS R));  DFT_R;  out[(j/NS) NS R + j%NS + r NS] = v[r]
-// TW: 0 none (NS = 1), 1 full table tw[(r-1) NS + k], 2 powers of tw[k] = exp(-2 pi i k / (NS R))
-template <int R, int NS, int TW, int NBATCH>
-__device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__ tw, int tid) {
-    constexpr int NB = kN / R;                                   // butterflies per FFT
-    constexpr int TOTAL = NB * NBATCH;
-    constexpr int PER = (TOTAL + kThreads - 1) / kThreads;
-    float2 v[PER][R];
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        const int idx = tid + u * kThreads;
-        if (idx < TOTAL) {
-            const int g = idx / NB, j = idx % NB, k = j % NS;
-            const float2* src = buf + g * kPad;
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[u][r] = src[padi(j + r * NB)];
-            if (TW == 1) {
-#pragma unroll
-                for (int r = 1; r < R; ++r) v[u][r] = cmul(v[u][r], tw[(r - 1) * NS + k]);
-            } else if (TW == 2) {
-                const float2 w1 = tw[k];
-                const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
-                const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
-                v[u][1] = cmul(v[u][1], w1); v[u][2] = cmul(v[u][2], w2); v[u][3] = cmul(v[u][3], w3);
-                v[u][4] = cmul(v[u][4], w4); v[u][5] = cmul(v[u][5], w5); v[u][6] = cmul(v[u][6], w6);
-                v[u][7] = cmul(v[u][7], w7);
-            }
-            Dft<R>::run(v[u]);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        const int idx = tid + u * kThreads;
-        if (idx < TOTAL) {
-            const int g = idx / NB, j = idx % NB, k = j % NS;
-            float2* dst = buf + g * kPad;
-            const int base = (j / NS) * NS * R + k;
-#pragma unroll
-            for (int r = 0; r < R; ++r) dst[padi(base + r * NS)] = v[u][r];
-        }
-    }
-    __syncthreads();
-}
-
-template <int NBATCH>
-__device__ __forceinline__ void fft1024(float2* buf, const float2* tw2, const float2* tw3, int tid) {
-    fft_pass<16, 1, 0, NBATCH>(buf, nullptr, tid);
-    fft_pass<8, 16, 1, NBATCH>(buf, tw2, tid);
-    fft_pass<8, 128, 2, NBATCH>(buf, tw3, tid);
-}
+constexpr int kP = 512;
 
 struct CfParams {
     const float* comb;         // [B, T]
@@ -119,7 +60,7 @@ __device__ __forceinline__ BinFilter make_filter(float hm, float hp, float nm) {
 constexpr size_t kSmemBytes = (size_t)2 * kPad * sizeof(float2) + (size_t)(kTw2 + kTw3) * sizeof(float2) +
                               (size_t)kN * sizeof(float);      // 17408 + 1920 + 4096 = 23424 B
 
-__global__ void __launch_bounds__(kThreads) combsubfast_kernel(CfParams p) {
+__global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);          // frame a: time -> spectrum -> pair spectrum -> pair time
     float2* bufB = bufA + kPad;                                  // frame b (must follow bufA: batched passes)
@@ -138,15 +79,7 @@ __global__ void __launch_bounds__(kThreads) combsubfast_kernel(CfParams p) {
 
     // ---- one-time tables ----
     for (int i = tid; i < kN; i += kThreads) win[i] = sqrtf(0.5f - 0.5f * cospif((float)i * (2.0f / kN)));
-    for (int i = tid; i < kTw2; i += kThreads) {
-        const int r = i / 16 + 1, k = i % 16;
-        float sn, cs; sincospif(-2.0f * (float)(r * k) / 128.0f, &sn, &cs);
-        tw2[i] = make_float2(cs, sn);
-    }
-    for (int i = tid; i < kTw3; i += kThreads) {
-        float sn, cs; sincospif(-2.0f * (float)i / 1024.0f, &sn, &cs);
-        tw3[i] = make_float2(cs, sn);
-    }
+    init_twiddles(tw2, tw3, tid);
     __syncthreads();
 
     // windowed (comb + j noise) of frame q into `buf`; samples outside [0, T) are the zero padding (:766,772)

@@ -482,8 +482,14 @@ namespace b2d {
 int ltv_fir_tc_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
                       int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
                       int nF, int P, cudaStream_t st);
+// FFT-domain evaluation (ltv_fir_fft.cu): block size 512, at most 512 taps per job
+bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs);
+int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
+                       int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
+                       int nF, int P, cudaStream_t st);
 
-// 0 = auto, 1 = CUDA-core kernel, 2 = tensor-core kernel (block size 512 only).
+// 0 = auto, 1 = CUDA-core kernel, 2 = tensor-core kernel (block size 512 only), 4 = FFT-domain kernel where it
+// applies (block size 512, <= 512 taps; other shapes fall through to the CUDA-core kernel).
 // auto = CUDA cores: measured on B200 (B=32 x 10 s, two 510-tap filters) the tcgen05 kernel takes
 // 4.20 ms against 1.26 ms -- with N = 8 columns every MMA re-reads its 4 KB Hankel operand from
 // shared memory for 16 kflop, so it is operand-bandwidth bound (~56 cycles per 128x8x8 MMA).
@@ -504,6 +510,13 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
     {
         const int impl = g_fir_impl;
         const bool tc_ok = (P == 512) && !(njobs == 2 && (taps1 != taps2 || addend));
+        if (impl == 4 && ltv_fir_fft_supported(P, taps1, taps2, njobs)) {
+            const float* ptrs0[] = {x1, x2, y1, y2, addend, mix};
+            for (const float* q : ptrs0)
+                if (q && !aligned16(q)) return fail(B2D_ERR_ALIGN, "ltv_fir: signal pointers must be 16-byte aligned");
+            if ((taps1 & 1) || (njobs == 2 && (taps2 & 1))) return fail(B2D_ERR_SHAPE, "ltv_fir: bad tap count");
+            return ltv_fir_fft_launch(x1, ir1, taps1, y1, x2, ir2, taps2, y2, addend, mix, seed, utt_off, B, nF, P, st);
+        }
         if (impl == 2 && !tc_ok) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: tensor-core kernel needs block size 512");
         if (impl == 2) {
             const float* ptrs0[] = {x1, x2, y1, y2, addend, mix};
@@ -569,8 +582,9 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
 }  // namespace b2d
 
 extern "C" int b2d_set_fir_impl(int impl) {
-    // 0 auto, 1 CUDA cores (auto variant), 2 tensor cores, 3 CUDA cores forcing the 8-outputs/thread scalar kernel
-    if (impl < 0 || impl > 3) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
+    // 0 auto, 1 CUDA cores (auto variant), 2 tensor cores, 3 CUDA cores forcing the 8-outputs/thread scalar kernel,
+    // 4 FFT domain (experimental until measured on hardware)
+    if (impl < 0 || impl > 4) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
     b2d::g_fir_impl = (impl == 3) ? 1 : impl;
     b2d::g_fir_variant = (impl == 3) ? 1 : 0;
     return 0;

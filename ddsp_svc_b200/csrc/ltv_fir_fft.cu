@@ -1,0 +1,278 @@
+// K4f: linear time-varying FIR evaluated in the FFT domain (alternative to the direct-form kernels of ltv_fir.cu).
+// Same contract as b2d::ltv_fir_launch (reference ddsp/core.py:120-182):
+//
+//   y[n] = sum_tau ((1-phi_m) h_f[tau] + phi_m h_{f+1}[tau]) x[m],   m = n + L/2 - tau, f = floor(m/P), phi_m = (m mod P)/P
+//
+// Regrouped by INPUT hop g (samples m = gP + i, i < P):   y = sum_g  x_g * h_g  +  (phi x_g) * (h_{g+1} - h_g)
+// -- two linear convolutions of a P-sample segment with L <= P taps, so a 2P = 1024-point FFT holds them without
+// wrap-around (P + L - 1 <= 1023).  A CTA walks the input hops of its chunk TWO at a time; per pair and job:
+//   * x_g and phi*x_g are real: one complex FFT of (x_g + j phi x_g) gives both spectra (split by conjugate
+//     symmetry); the impulse responses of frames g+1 and g+2 share one FFT the same way (frame g's spectrum is kept
+//     in registers from the previous pair);
+//   * Y_g = X_g H_g + XU_g (H_{g+1} - H_g) and Y_{g+1} likewise are spectra of real segments: one inverse FFT of
+//     Y_g + j Y_{g+1} returns both.  Only signals of the SAME job are ever paired in one transform, so the fp32
+//     round-off of a loud channel (harmonic) never leaks into a quiet one (filtered noise);
+//   * all forward transforms of a pair (2 inputs + 1 impulse-response pair per job) run as one batch through the
+//     shared-memory Stockham passes of fft1024.cuh, then all inverse transforms as a second batch;
+//   * every 1021-sample output segment is overlap-added into a 4-hop ring per job at its delay-compensated position;
+//     a hop is complete once the segment of the FOLLOWING input hop has been added and is then written exactly once
+//     (y1, y2 and mix = y1 + y2 (+ addend)) with 128-bit stores -- deterministic, no atomics.
+// 4 FFT-1024 per hop and job pair replace 2 x 2 x L x P = 1.04 M FMAs of the direct form (L = 510): ~4x fewer
+// instructions.  A CTA owns G hops of one utterance and processes the G+2 input hops that reach them; white-noise
+// input (x2 == nullptr) is the same Philox stream as in the direct-form kernels.
+//
+// STATUS: selected with b2d_set_fir_impl(4); NOT the default until it has been measured on hardware.  Logic pinned by
+// the host emulation in tests/emu/ (tests/test_emu_ltv_fir_fft.py).
+#ifndef B2D_HOST_EMU
+#include "b2d_common.cuh"
+#endif
+#include "fft1024.cuh"
+
+using namespace b2d_fft1024;
+
+namespace {
+
+constexpr int kHop = 512;
+constexpr int kRing = 4 * kHop;          // power of two: slot = (t - t_lo) & (kRing - 1)
+
+struct FftFirJob {
+    const float* x;    // [B, T] or nullptr -> in-kernel uniform noise
+    const float* ir;   // [B, nF, L]
+    float* y;          // [B, T] or nullptr
+    int L;
+};
+
+struct FftFirParams {
+    FftFirJob job[2];
+    const float* addend;
+    float* mix;
+    unsigned long long seed;
+    long long utt_off;
+    int nF, G;
+};
+
+template <int NJ> constexpr size_t fir_fft_smem() {
+    return (size_t)3 * NJ * kPad * sizeof(float2) + (size_t)(kTw2 + kTw3) * sizeof(float2) + (size_t)NJ * kRing * sizeof(float);
+}   // NJ = 2: 52224 + 1920 + 16384 = 70528 B (3 CTAs per SM);  NJ = 1: 36224 B
+
+// spectra of two real sequences a, c from Z = FFT(a + j c):  A[k] = (Z[k] + conj Z[N-k]) / 2,  C[k] = (Z[k] - conj Z[N-k]) / 2j
+__device__ __forceinline__ void split2(float2 zk, float2 zm, float2& A, float2& C) {
+    A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    C = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // buffer b of the batch lives at F + b * kPad:  XA(j) = j  (hop g; later the paired output of job j),
+    // XB(j) = NJ + j (hop g+1),  HH(j) = 2 NJ + j (impulse responses of frames g+1 and g+2)
+    float2* F = reinterpret_cast<float2*>(smem_raw);
+    float2* tw2 = F + 3 * NJ * kPad;
+    float2* tw3 = tw2 + kTw2;
+    float* ring = reinterpret_cast<float*>(tw3 + kTw3);          // [NJ][kRing]
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int nF = p.nF, T = nF * kHop;
+    const int h0 = blockIdx.x * p.G, h1 = min(h0 + p.G, nF);
+    const int t_lo = h0 * kHop, t_hi = h1 * kHop;
+    const unsigned long long utt = (unsigned long long)(p.utt_off + b);
+
+    init_twiddles(tw2, tw3, tid);
+    for (int i = tid; i < NJ * kRing; i += kThreads) ring[i] = 0.f;
+
+    // (h_j[fa], h_j[fb]) as one complex sequence, zero-padded to 1024; frame indices clamp (h_{nF} := h_{nF-1})
+    auto load_ir_pair = [&](int j, int fa, int fb, bool with_b) {
+        const int L = p.job[j].L;
+        const float* base = p.job[j].ir + (size_t)b * nF * L;
+        const float* ra = base + (size_t)min(max(fa, 0), nF - 1) * L;
+        const float* rb = base + (size_t)min(max(fb, 0), nF - 1) * L;
+        float2* buf = F + (2 * NJ + j) * kPad;
+#pragma unroll
+        for (int u = 0; u < kN / kThreads; ++u) {
+            const int tau = tid + u * kThreads;
+            const bool in = tau < L;
+            buf[padi(tau)] = make_float2(in ? __ldg(ra + tau) : 0.f, (in && with_b) ? __ldg(rb + tau) : 0.f);
+        }
+    };
+    // x_j[gP + i] (1 + j i/P) for i < P, zeros above; `present` false -> all zeros (hop outside the chunk's reach)
+    auto load_x = [&](int j, int g, bool present, float2* buf) {
+        const int i0 = tid << 2;
+        const int m0 = g * kHop + i0;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (present) {
+            if (p.job[j].x) v = __ldg(reinterpret_cast<const float4*>(p.job[j].x + (size_t)b * T + m0));
+            else v = b2d::philox_uniform_pm1(p.seed, utt, (uint32_t)(m0 >> 2));
+        }
+        const float s = 1.0f / kHop;
+        buf[padi(i0 + 0)] = make_float2(v.x, v.x * ((float)(i0 + 0) * s));
+        buf[padi(i0 + 1)] = make_float2(v.y, v.y * ((float)(i0 + 1) * s));
+        buf[padi(i0 + 2)] = make_float2(v.z, v.z * ((float)(i0 + 2) * s));
+        buf[padi(i0 + 3)] = make_float2(v.w, v.w * ((float)(i0 + 3) * s));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) buf[padi(kHop + i0 + e)] = make_float2(0.f, 0.f);
+    };
+
+    // spectrum of frame g per job: bins k = tid + 128 u; thread 0 additionally holds DC (u = 0) and Nyquist (real)
+    float2 Hp[NJ][4];
+    float HpN[NJ];
+    const int gs = max(h0 - 1, 0), ge = min(h1, nF - 1);
+
+    // ---- prologue: spectra of frame gs ----
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs, gs, false);
+    __syncthreads();
+    fft1024<NJ>(F + 2 * NJ * kPad, tw2, tw3, tid);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float2* H = F + (2 * NJ + j) * kPad;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = tid + u * kThreads;
+            float2 unused;
+            if (k == 0) Hp[j][u] = make_float2(H[padi(0)].x, 0.f);
+            else split2(H[padi(k)], H[padi(kN - k)], Hp[j][u], unused);
+        }
+        HpN[j] = H[padi(kHop)].x;                                   // only thread 0 uses it
+    }
+    __syncthreads();
+
+    // write hop h (complete) from the rings: y_j, mix; clear its ring slots
+    auto emit = [&](int h) {
+        const int slot = (((h - h0) * kHop) & (kRing - 1)) + (tid << 2);
+        const size_t o = (size_t)b * T + (size_t)h * kHop + (tid << 2);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float4* r = reinterpret_cast<float4*>(ring + j * kRing + slot);
+            const float4 v = *r;
+            *r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.job[j].y) b2d::st_global_v4(p.job[j].y + o, v);
+            if (j == 0) m = v;
+            else { m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w; }
+        }
+        if (p.mix) {
+            if (p.addend) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.addend + o));
+                m.x += a.x; m.y += a.y; m.z += a.z; m.w += a.w;
+            }
+            b2d::st_global_v4(p.mix + o, m);
+        }
+    };
+
+#pragma unroll 1
+    for (int g = gs; g <= ge; g += 2) {
+        const bool has_b = g + 1 <= ge;
+        // ---- forward: both hops of every job and the impulse-response pairs as one batch ----
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            load_x(j, g, true, F + j * kPad);
+            load_x(j, g + 1, has_b, F + (NJ + j) * kPad);
+            load_ir_pair(j, g + 1, g + 2, true);
+        }
+        __syncthreads();
+        fft1024<3 * NJ>(F, tw2, tw3, tid);
+
+        // ---- Y_g = X_g H_g + XU_g (H_{g+1} - H_g),  Y_{g+1} = X_{g+1} H_{g+1} + XU_{g+1} (H_{g+2} - H_{g+1});
+        //      paired as Y_g + j Y_{g+1} (Hermitian extension), stored re/im-swapped over XA(j) ----
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float2* XA = F + j * kPad;
+            const float2* XB = F + (NJ + j) * kPad;
+            const float2* HH = F + (2 * NJ + j) * kPad;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = tid + u * kThreads;
+                if (k == 0) continue;
+                const int ik = padi(k), im = padi(kN - k);
+                float2 Xa, XUa, Xb, XUb, Ha, Hb;
+                split2(XA[ik], XA[im], Xa, XUa);
+                split2(XB[ik], XB[im], Xb, XUb);
+                split2(HH[ik], HH[im], Ha, Hb);
+                const float2 ya = cadd(cmul(Xa, Hp[j][u]), cmul(XUa, csub(Ha, Hp[j][u])));
+                const float2 yb = cadd(cmul(Xb, Ha), cmul(XUb, csub(Hb, Ha)));
+                // Y[k] = ya + j yb;  Y[N-k] = conj(ya) + j conj(yb);  stored as (im, re)
+                XA[ik] = make_float2(ya.y + yb.x, ya.x - yb.y);
+                XA[im] = make_float2(yb.x - ya.y, ya.x + yb.y);
+                Hp[j][u] = Hb;
+            }
+            if (tid == 0) {      // DC and Nyquist: every spectrum involved is real there
+                const float2 a0 = XA[padi(0)], b0 = XB[padi(0)], z0 = HH[padi(0)];           // (X, XU), (X, XU), (H_{g+1}, H_{g+2})
+                const float2 aN = XA[padi(kHop)], bN = XB[padi(kHop)], zN = HH[padi(kHop)];
+                const float hp0 = Hp[j][0].x, hpN = HpN[j];
+                const float ya0 = fmaf(a0.y, z0.x - hp0, a0.x * hp0), yb0 = fmaf(b0.y, z0.y - z0.x, b0.x * z0.x);
+                const float yaN = fmaf(aN.y, zN.x - hpN, aN.x * hpN), ybN = fmaf(bN.y, zN.y - zN.x, bN.x * zN.x);
+                XA[padi(0)] = make_float2(yb0, ya0);
+                XA[padi(kHop)] = make_float2(ybN, yaN);
+                Hp[j][0] = make_float2(z0.y, 0.f);
+                HpN[j] = zN.y;
+            }
+        }
+        __syncthreads();
+
+        // ---- inverse of the pairs (batch over jobs): hop g = stored .y / N, hop g+1 = stored .x / N ----
+        fft1024<NJ>(F, tw2, tw3, tid);
+
+        // ---- overlap-add at the delay-compensated positions t = gP - L/2 + n (hop g) and + P (hop g+1), kept to this
+        //      CTA's hops.  Slots hit twice (n and n - P) belong to the same thread: no race. ----
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float2* Y = F + j * kPad;
+            float* rj = ring + j * kRing;
+            const int base = g * kHop - (p.job[j].L >> 1) - t_lo;
+#pragma unroll
+            for (int u = 0; u < kN / kThreads; ++u) {
+                const int n = tid + u * kThreads;
+                const float2 v = Y[padi(n)];
+                const int ra = base + n, rb = ra + kHop;
+                if (ra >= 0 && ra < t_hi - t_lo) rj[ra & (kRing - 1)] += v.y * (1.0f / kN);
+                if (has_b && rb >= 0 && rb < t_hi - t_lo) rj[rb & (kRing - 1)] += v.x * (1.0f / kN);
+            }
+        }
+        __syncthreads();
+        // complete now: every hop below the last input hop just added
+        if (g - 1 >= h0) emit(g - 1);
+        if (has_b && g >= h0) emit(g);
+        __syncthreads();
+    }
+    if (ge < h1) emit(ge);                        // last hop of the utterance: no following input hop
+}
+
+}  // namespace
+
+#ifndef B2D_HOST_EMU
+namespace b2d {
+
+bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs) {
+    return P == kHop && taps1 > 0 && taps1 <= kHop && (njobs == 1 || (taps2 > 0 && taps2 <= kHop));
+}
+
+int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
+                       int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
+                       int nF, int P, cudaStream_t st) {
+    const int njobs = ir2 ? 2 : 1;
+    if (!ltv_fir_fft_supported(P, taps1, taps2, njobs))
+        return fail(B2D_ERR_UNSUPPORTED, "ltv_fir(fft): needs block size %d and at most %d taps", kHop, kHop);
+    FftFirParams p;
+    p.job[0] = {x1, ir1, y1, taps1};
+    p.job[1] = {x2, ir2, y2, njobs == 2 ? taps2 : taps1};
+    p.addend = addend; p.mix = mix; p.seed = seed; p.utt_off = utt_off; p.nF = nF; p.G = 32;
+    const dim3 grid((unsigned)((nF + p.G - 1) / p.G), B);
+    if (njobs == 2) {
+        constexpr size_t smem = fir_fft_smem<2>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
+            cudaFuncSetAttribute(ltv_fir_fft_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr_set = true;
+        }
+        ltv_fir_fft_kernel<2><<<grid, kThreads, smem, st>>>(p);
+    } else {
+        ltv_fir_fft_kernel<1><<<grid, kThreads, fir_fft_smem<1>(), st>>>(p);
+    }
+    return check_launch("ltv_fir(fft)");
+}
+
+}  // namespace b2d
+#endif  // B2D_HOST_EMU

@@ -19,8 +19,9 @@ _tables_lock = threading.Lock()
 
 
 def set_fir_impl(impl):
-    """'auto' / 'cuda' (CUDA-core kernel, the default) or 'tc' (tcgen05 3xTF32 kernel, block size 512)."""
-    _lib.check(_lib.lib().b2d_set_fir_impl({"auto": 0, "cuda": 1, "tc": 2, "cuda8": 3}[impl]), "b2d_set_fir_impl")
+    """'auto' / 'cuda' (CUDA-core kernel, the default), 'tc' (tcgen05 3xTF32 kernel, block size 512), 'cuda8' (older
+    scalar CUDA-core kernel) or 'fft' (FFT-domain kernel, experimental: not yet measured on hardware)."""
+    _lib.check(_lib.lib().b2d_set_fir_impl({"auto": 0, "cuda": 1, "tc": 2, "cuda8": 3, "fft": 4}[impl]), "b2d_set_fir_impl")
 
 
 def set_ir_impl(impl):
