@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
         // complete now: every hop below the last input hop just added
         if (g - 1 >= h0) emit(g - 1);
         if (has_b && g >= h0) emit(g);
-        __syncthreads();
+        // no barrier needed here: emit touches only the rings, the next iteration's loads only F (whose last reads
+        // were ordered by the barrier above), and the rings are next written after the FFT passes' barriers
     }
     if (ge < h1) emit(ge);                        // last hop of the utterance: no following input hop
 }
