@@ -482,14 +482,14 @@ namespace b2d {
 int ltv_fir_tc_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
                       int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
                       int nF, int P, cudaStream_t st);
-// FFT-domain evaluation (ltv_fir_fft.cu): block size 512, at most 512 taps per job
+// FFT-domain evaluation (ltv_fir_fft.cu): block size 512, at most 1024 taps per job
 bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs);
 int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
                        int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
                        int nF, int P, cudaStream_t st);
 
 // 0 = auto, 1 = CUDA-core kernel, 2 = tensor-core kernel (block size 512 only), 4 = FFT-domain kernel where it
-// applies (block size 512, <= 512 taps; other shapes fall through to the CUDA-core kernel).
+// applies (block size 512, <= 1024 taps; other shapes fall through to the CUDA-core kernel).
 // auto = CUDA cores: measured on B200 (B=32 x 10 s, two 510-tap filters) the tcgen05 kernel takes
 // 4.20 ms against 1.26 ms -- with N = 8 columns every MMA re-reads its 4 KB Hankel operand from
 // shared memory for 16 kflop, so it is operand-bandwidth bound (~56 cycles per 128x8x8 MMA).

@@ -4,8 +4,9 @@
 //   y[n] = sum_tau ((1-phi_m) h_f[tau] + phi_m h_{f+1}[tau]) x[m],   m = n + L/2 - tau, f = floor(m/P), phi_m = (m mod P)/P
 //
 // Regrouped by INPUT hop g (samples m = gP + i, i < P):   y = sum_g  x_g * h_g  +  (phi x_g) * (h_{g+1} - h_g)
-// -- two linear convolutions of a P-sample segment with L <= P taps, so a 2P = 1024-point FFT holds them without
-// wrap-around (P + L - 1 <= 1023).  A CTA walks the input hops of its chunk TWO at a time; per pair and job:
+// -- two linear convolutions of a P-sample segment with L taps, which an N-point FFT holds without wrap-around when
+// P + L - 1 <= N: N = 1024 for L <= 512 (Sins, CombSub's all-pass and noise filters), N = 2048 for L <= 1024 (CombSub's
+// 1022-tap harmonic filter).  A CTA walks the input hops of its chunk TWO at a time; per pair and job:
 //   * x_g and phi*x_g are real: one complex FFT of (x_g + j phi x_g) gives both spectra (split by conjugate
 //     symmetry); the impulse responses of frames g+1 and g+2 share one FFT the same way (frame g's spectrum is kept
 //     in registers from the previous pair);
@@ -26,9 +27,9 @@
 #ifndef B2D_HOST_EMU
 #include "b2d_common.cuh"
 #endif
-#include "fft1024.cuh"
+#include "fft_smem.cuh"
 
-using namespace b2d_fft1024;
+using namespace b2d_fft_smem;
 
 namespace {
 
@@ -51,9 +52,10 @@ struct FftFirParams {
     int nF, G;
 };
 
-template <int NJ> constexpr size_t fir_fft_smem() {
-    return (size_t)3 * NJ * kPad * sizeof(float2) + (size_t)(kTw2 + kTw3) * sizeof(float2) + (size_t)NJ * kRing * sizeof(float);
-}   // NJ = 2: 52224 + 1920 + 16384 = 70528 B (3 CTAs per SM);  NJ = 1: 36224 B
+template <int N, int NJ> constexpr size_t fir_fft_smem() {
+    return (size_t)3 * NJ * Plan<N>::kPad * sizeof(float2) + (size_t)(Plan<N>::kTw2 + Plan<N>::kTw3) * sizeof(float2) +
+           (size_t)NJ * kRing * sizeof(float);
+}   // N = 1024: NJ = 2 -> 70528 B (3 CTAs per SM), NJ = 1 -> 36224 B;  N = 2048: NJ = 1 -> 64384 B, NJ = 2 -> 124800 B
 
 // spectra of two real sequences a, c from Z = FFT(a + j c):  A[k] = (Z[k] + conj Z[N-k]) / 2,  C[k] = (Z[k] - conj Z[N-k]) / 2j
 __device__ __forceinline__ void split2(float2 zk, float2 zm, float2& A, float2& C) {
@@ -61,8 +63,10 @@ __device__ __forceinline__ void split2(float2 zk, float2 zm, float2& A, float2& 
     C = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
 }
 
-template <int NJ>
-__global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p) {
+template <int N, int NJ>
+__global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_fir_fft_kernel(FftFirParams p) {
+    constexpr int kN = N, kPad = Plan<N>::kPad, kTw2 = Plan<N>::kTw2, kTw3 = Plan<N>::kTw3;
+    constexpr int kBins = N / 2 / kThreads;          // bins k = tid + 128 u per thread (DC.. N/2-1); Nyquist on thread 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // buffer b of the batch lives at F + b * kPad:  XA(j) = j  (hop g; later the paired output of job j),
     // XB(j) = NJ + j (hop g+1),  HH(j) = 2 NJ + j (impulse responses of frames g+1 and g+2)
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
     const int t_lo = h0 * kHop, t_hi = h1 * kHop;
     const unsigned long long utt = (unsigned long long)(p.utt_off + b);
 
-    init_twiddles(tw2, tw3, tid);
+    init_twiddles<N>(tw2, tw3, tid);
     for (int i = tid; i < NJ * kRing; i += kThreads) ring[i] = 0.f;
 
     // (h_j[fa], h_j[fb]) as one complex sequence, zero-padded to 1024; frame indices clamp (h_{nF} := h_{nF-1})
@@ -110,11 +114,13 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
         buf[padi(i0 + 2)] = make_float2(v.z, v.z * ((float)(i0 + 2) * s));
         buf[padi(i0 + 3)] = make_float2(v.w, v.w * ((float)(i0 + 3) * s));
 #pragma unroll
-        for (int e = 0; e < 4; ++e) buf[padi(kHop + i0 + e)] = make_float2(0.f, 0.f);
+        for (int z = kHop; z < kN; z += kHop)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) buf[padi(z + i0 + e)] = make_float2(0.f, 0.f);
     };
 
     // spectrum of frame g per job: bins k = tid + 128 u; thread 0 additionally holds DC (u = 0) and Nyquist (real)
-    float2 Hp[NJ][4];
+    float2 Hp[NJ][kBins];
     float HpN[NJ];
     const int gs = max(h0 - 1, 0), ge = min(h1, nF - 1);
 
@@ -122,18 +128,18 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
 #pragma unroll
     for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs, gs, false);
     __syncthreads();
-    fft1024<NJ>(F + 2 * NJ * kPad, tw2, tw3, tid);
+    fft_forward<N, NJ>(F + 2 * NJ * kPad, tw2, tw3, tid);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const float2* H = F + (2 * NJ + j) * kPad;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kBins; ++u) {
             const int k = tid + u * kThreads;
             float2 unused;
             if (k == 0) Hp[j][u] = make_float2(H[padi(0)].x, 0.f);
             else split2(H[padi(k)], H[padi(kN - k)], Hp[j][u], unused);
         }
-        HpN[j] = H[padi(kHop)].x;                                   // only thread 0 uses it
+        HpN[j] = H[padi(kN / 2)].x;                                 // only thread 0 uses it
     }
     __syncthreads();
 
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
             load_ir_pair(j, g + 1, g + 2, true);
         }
         __syncthreads();
-        fft1024<3 * NJ>(F, tw2, tw3, tid);
+        fft_forward<N, 3 * NJ>(F, tw2, tw3, tid);
 
         // ---- Y_g = X_g H_g + XU_g (H_{g+1} - H_g),  Y_{g+1} = X_{g+1} H_{g+1} + XU_{g+1} (H_{g+2} - H_{g+1});
         //      paired as Y_g + j Y_{g+1} (Hermitian extension), stored re/im-swapped over XA(j) ----
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
             const float2* XB = F + (NJ + j) * kPad;
             const float2* HH = F + (2 * NJ + j) * kPad;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kBins; ++u) {
                 const int k = tid + u * kThreads;
                 if (k == 0) continue;
                 const int ik = padi(k), im = padi(kN - k);
@@ -198,12 +204,12 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
             }
             if (tid == 0) {      // DC and Nyquist: every spectrum involved is real there
                 const float2 a0 = XA[padi(0)], b0 = XB[padi(0)], z0 = HH[padi(0)];           // (X, XU), (X, XU), (H_{g+1}, H_{g+2})
-                const float2 aN = XA[padi(kHop)], bN = XB[padi(kHop)], zN = HH[padi(kHop)];
+                const float2 aN = XA[padi(kN / 2)], bN = XB[padi(kN / 2)], zN = HH[padi(kN / 2)];
                 const float hp0 = Hp[j][0].x, hpN = HpN[j];
                 const float ya0 = fmaf(a0.y, z0.x - hp0, a0.x * hp0), yb0 = fmaf(b0.y, z0.y - z0.x, b0.x * z0.x);
                 const float yaN = fmaf(aN.y, zN.x - hpN, aN.x * hpN), ybN = fmaf(bN.y, zN.y - zN.x, bN.x * zN.x);
                 XA[padi(0)] = make_float2(yb0, ya0);
-                XA[padi(kHop)] = make_float2(ybN, yaN);
+                XA[padi(kN / 2)] = make_float2(ybN, yaN);
                 Hp[j][0] = make_float2(z0.y, 0.f);
                 HpN[j] = zN.y;
             }
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
         __syncthreads();
 
         // ---- inverse of the pairs (batch over jobs): hop g = stored .y / N, hop g+1 = stored .x / N ----
-        fft1024<NJ>(F, tw2, tw3, tid);
+        fft_forward<N, NJ>(F, tw2, tw3, tid);
 
         // ---- overlap-add at the delay-compensated positions t = gP - L/2 + n (hop g) and + P (hop g+1), kept to this
         //      CTA's hops.  Slots hit twice (n and n - P) belong to the same thread: no race. ----
@@ -244,8 +250,26 @@ __global__ void __launch_bounds__(kThreads, 3) ltv_fir_fft_kernel(FftFirParams p
 #ifndef B2D_HOST_EMU
 namespace b2d {
 
+// block size 512; both jobs' tap counts decide the transform size: <= 512 -> 1024 points, <= 1024 -> 2048 points
 bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs) {
-    return P == kHop && taps1 > 0 && taps1 <= kHop && (njobs == 1 || (taps2 > 0 && taps2 <= kHop));
+    const int tmax = njobs == 2 ? (taps1 > taps2 ? taps1 : taps2) : taps1;
+    return P == kHop && taps1 > 0 && (njobs == 1 || taps2 > 0) && tmax <= 1024;
+}
+
+template <int N, int NJ>
+static int launch_fir_fft(const FftFirParams& p, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = fir_fft_smem<N, NJ>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
+        }
+        cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+    ltv_fir_fft_kernel<N, NJ><<<grid, kThreads, smem, st>>>(p);
+    return check_launch("ltv_fir(fft)");
 }
 
 int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
@@ -253,26 +277,15 @@ int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, 
                        int nF, int P, cudaStream_t st) {
     const int njobs = ir2 ? 2 : 1;
     if (!ltv_fir_fft_supported(P, taps1, taps2, njobs))
-        return fail(B2D_ERR_UNSUPPORTED, "ltv_fir(fft): needs block size %d and at most %d taps", kHop, kHop);
+        return fail(B2D_ERR_UNSUPPORTED, "ltv_fir(fft): needs block size %d and at most 1024 taps", kHop);
     FftFirParams p;
     p.job[0] = {x1, ir1, y1, taps1};
     p.job[1] = {x2, ir2, y2, njobs == 2 ? taps2 : taps1};
     p.addend = addend; p.mix = mix; p.seed = seed; p.utt_off = utt_off; p.nF = nF; p.G = 32;
     const dim3 grid((unsigned)((nF + p.G - 1) / p.G), B);
-    if (njobs == 2) {
-        constexpr size_t smem = fir_fft_smem<2>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
-            cudaFuncSetAttribute(ltv_fir_fft_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            attr_set = true;
-        }
-        ltv_fir_fft_kernel<2><<<grid, kThreads, smem, st>>>(p);
-    } else {
-        ltv_fir_fft_kernel<1><<<grid, kThreads, fir_fft_smem<1>(), st>>>(p);
-    }
-    return check_launch("ltv_fir(fft)");
+    const int tmax = njobs == 2 ? (taps1 > taps2 ? taps1 : taps2) : taps1;
+    if (tmax <= kHop) return njobs == 2 ? launch_fir_fft<1024, 2>(p, grid, st) : launch_fir_fft<1024, 1>(p, grid, st);
+    return njobs == 2 ? launch_fir_fft<2048, 2>(p, grid, st) : launch_fir_fft<2048, 1>(p, grid, st);
 }
 
 }  // namespace b2d

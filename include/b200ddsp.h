@@ -119,8 +119,8 @@ int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1,
  * cores, 3 = CUDA cores forcing the older 8-outputs-per-thread scalar-FFMA kernel (the default
  * CUDA-core kernel for block sizes that are multiples of 512 uses 16 outputs per thread and packed
  * fma.rn.f32x2), 4 = FFT-domain evaluation (ltv_fir_fft.cu: per input hop one 1024-point FFT per signal, the
- * impulse responses' spectra, and one inverse FFT per pair of hops; block size 512 and <= 512 taps, other shapes
- * use the CUDA-core kernel; ~4x fewer instructions than the direct form.  EXPERIMENTAL: pinned by a CPU run of the
+ * impulse responses' spectra, and one inverse FFT per pair of hops, 2048 points above 512 taps; block size 512 and
+ * <= 1024 taps, other shapes use the CUDA-core kernel; ~4x fewer instructions than the direct form.  EXPERIMENTAL: pinned by a CPU run of the
  * kernel source (tests/emu/), not yet measured on hardware, therefore not the default).
  * Process-wide test/diagnostic knob. */
 int b2d_set_fir_impl(int impl);

@@ -37,6 +37,11 @@ int main(int argc, char** argv) {
     emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), x2.data(), ir2.data(), L, y2.data(), add.data(), mix.data(), 1, 0, B, nF, 3);
     emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), nullptr, ir2.data(), 254, y2.data(), nullptr, mix.data(), 1, 0, B, nF, 32);
     emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), nullptr, nullptr, 0, nullptr, nullptr, mix.data(), 1, 0, B, nF, 2);
+    {   // 2048-point instance (1022 taps)
+        std::vector<float> irl(B * nF * 1022);
+        fill(irl, 0.03f);
+        emu_ltv_fir_fft(x1.data(), irl.data(), 1022, y1.data(), nullptr, nullptr, 0, nullptr, nullptr, mix.data(), 1, 0, B, nF, 4);
+    }
     for (float v : mix) s += v;
 #elif defined(TSAN_CSFAST)
     const int B = 1, nF = 6, T = nF * 512, C = 3 * 513;

@@ -74,7 +74,7 @@ def test_one_job_matches_closed_form(emu, nF, hops):
     assert np.array_equal(out["mix"], out["y1"])
 
 
-@pytest.mark.parametrize("L1,L2", [(510, 510), (510, 254), (128, 512), (2, 2)])
+@pytest.mark.parametrize("L1,L2", [(510, 510), (510, 254), (128, 512), (2, 2), (1022, 510), (514, 1024)])
 def test_two_jobs_mix_and_addend(emu, L1, L2):
     nF = 9
     x1, ir1 = _case(2, nF, L1, 1)
@@ -119,3 +119,25 @@ def test_in_kernel_noise_is_shard_invariant(emu):
     part = emu(x1[1:], ir1[1:], None, ir2[1:], seed=7, utt_off=1)
     assert np.array_equal(full["y2"][1:], part["y2"]) and np.array_equal(full["mix"][1:], part["mix"])
     assert 1e-3 < util.rms(full["y2"]) < 10 and np.isfinite(full["mix"]).all()
+
+
+@pytest.mark.parametrize("nF,hops,L", [(1, 32, 1022), (5, 2, 1022), (34, 32, 1022), (6, 32, 1024), (6, 3, 514)])
+def test_one_job_long_filters_use_the_2048_point_transform(emu, nF, hops, L):
+    """CombSub's 1022-tap harmonic filter: 512 + L - 1 > 1024, so the 2048-point instance runs"""
+    x, ir = _case(2, nF, L, 10 + nF)
+    out = emu(x, ir, hops=hops, want=("y1",))
+    truth = cf.ltv_fir(x.astype(np.float64), ir.astype(np.float64), P)
+    assert not np.isnan(out["y1"]).any()
+    assert util.rms(out["y1"] - truth) < 2e-7 * max(util.rms(truth), 1.0) and np.abs(out["y1"] - truth).max() < 5e-6
+
+
+def test_combsub_harmonic_filter_against_the_reference_port(emu):
+    """dynamic-window 1022-tap impulse responses as CombSub builds them, against the port that is bit-identical to
+    the live reference"""
+    from oracle import torch_port as tp
+    from tests.golden import cases as G
+    name = "combsub_b2_f24"
+    ref = util.port_outputs(name, G.build_inputs(name))
+    out = emu(ref["allpassed"].numpy(), ref["ir_harmonic"].numpy(), want=("y1",))
+    e = util.rms(out["y1"] - ref["harmonic"].numpy())
+    assert e < 5e-7 * util.rms(ref["harmonic"].numpy()) + 1e-9, e

@@ -68,6 +68,17 @@ def test_forward_through_fft_fir_matches_golden(name):
     assert e < 2e-6
 
 
+def test_fft_1022_taps_uses_the_2048_point_transform():
+    name = "combsub_b2_f24"
+    ref = util.port_outputs(name, G.build_inputs(name))
+    x, ir = ref["allpassed"].to(DEV), ref["ir_harmonic"].to(DEV).contiguous()
+    ops.set_fir_impl("fft")
+    y = ops.ltv_fir(x, ir, P).cpu()
+    e = util.rms(y - ref["harmonic"])
+    report.record("fir_fft/1022", rms=e, ref_rms=util.rms(ref["harmonic"]))
+    assert e < 5e-7 * util.rms(ref["harmonic"]) + 1e-9
+
+
 def test_fft_full_size_vs_cuda_and_in_kernel_noise():
     B, nF = 32, 861
     g = torch.Generator().manual_seed(3)
