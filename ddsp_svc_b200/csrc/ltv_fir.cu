@@ -29,6 +29,8 @@
 // addend), so signal = harmonic + noise (ddsp/vocoder.py:609) needs no extra pass.
 // White noise input is generated in-kernel (Philox4x32-10) when the job has no input pointer.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "b2d_common.cuh"
 
@@ -488,14 +490,26 @@ int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, 
                        int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
                        int nF, int P, cudaStream_t st);
 
-// 0 = auto, 1 = CUDA-core kernel, 2 = tensor-core kernel (block size 512 only), 4 = FFT-domain kernel where it
-// applies (block size 512, <= 1024 taps; other shapes fall through to the CUDA-core kernel).
+// 0 = auto (FFT-domain kernel where it applies, else CUDA cores), 1 = CUDA-core kernel, 2 = tensor-core kernel
+// (block size 512 only), 4 = FFT-domain kernel where it applies (block size 512, <= 1024 taps; other shapes fall
+// through to the CUDA-core kernel).
 // auto = CUDA cores: measured on B200 (B=32 x 10 s, two 510-tap filters) the tcgen05 kernel takes
 // 4.20 ms against 1.26 ms -- with N = 8 columns every MMA re-reads its 4 KB Hankel operand from
 // shared memory for 16 kflop, so it is operand-bandwidth bound (~56 cycles per 128x8x8 MMA).
 static int g_fir_impl = 0;
 // CUDA-core variant: 0 = auto (16 outputs/thread + FFMA2 when the block size is a multiple of 512), 1 = 8 outputs/thread scalar
 static int g_fir_variant = 0;
+
+// what "auto" means: the FFT-domain kernel wherever it applies (block size 512, <= 1024 taps; measured on B200:
+// 0.372 ms against 1.18 ms for Sins' two 510-tap filters, B = 32 x 10 s), the CUDA-core kernel otherwise.
+// B2D_FIR_AUTO=cuda in the environment restores the direct form as the automatic choice (A/B runs of whole programs).
+static int fir_auto_impl() {
+    static const int v = [] {
+        const char* e = getenv("B2D_FIR_AUTO");
+        return (e && (!strcmp(e, "cuda") || !strcmp(e, "1"))) ? 1 : 4;
+    }();
+    return v;
+}
 
 // internal entry (also used by the CombSub driver): mix = y1 (+ y2) (+ addend)
 int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
@@ -508,7 +522,7 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
     if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: batch %d > 65535", B);
     const int njobs = ir2 ? 2 : 1;
     {
-        const int impl = g_fir_impl;
+        const int impl = g_fir_impl == 0 ? fir_auto_impl() : g_fir_impl;
         const bool tc_ok = (P == 512) && !(njobs == 2 && (taps1 != taps2 || addend));
         if (impl == 4 && ltv_fir_fft_supported(P, taps1, taps2, njobs)) {
             const float* ptrs0[] = {x1, x2, y1, y2, addend, mix};
@@ -583,7 +597,7 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
 
 extern "C" int b2d_set_fir_impl(int impl) {
     // 0 auto, 1 CUDA cores (auto variant), 2 tensor cores, 3 CUDA cores forcing the 8-outputs/thread scalar kernel,
-    // 4 FFT domain (experimental until measured on hardware)
+    // 4 FFT domain
     if (impl < 0 || impl > 4) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
     b2d::g_fir_impl = (impl == 3) ? 1 : impl;
     b2d::g_fir_variant = (impl == 3) ? 1 : 0;

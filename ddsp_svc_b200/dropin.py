@@ -40,7 +40,7 @@ _MODEL_TYPES = {
         sampling_rate=a.data.sampling_rate, block_size=a.data.block_size, n_mag_allpass=a.model.n_mag_allpass,
         n_mag_harmonic=a.model.n_mag_harmonic, n_mag_noise=a.model.n_mag_noise,
         n_unit=a.data.encoder_out_channels, n_spk=a.model.n_spk),
-    "CombSubFast": lambda a: vocoder.CombSubFast(            # experimental, see vocoder.CombSubFast
+    "CombSubFast": lambda a: vocoder.CombSubFast(
         sampling_rate=a.data.sampling_rate, block_size=a.data.block_size,
         n_unit=a.data.encoder_out_channels, n_spk=a.model.n_spk),
     "CombSubSuperFast": lambda a: vocoder.CombSubSuperFast(
@@ -70,12 +70,11 @@ def load_model(model_path, device="cuda"):
     return model, args
 
 
-def patch_reference(experimental=False):
+def patch_reference():
     """Swap the synthesizer classes inside the (importable) reference package.  Returns the dict
-    of original classes so a caller can restore them.  ``experimental=True`` also swaps ``CombSubFast``,
-    whose kernel has not been validated on hardware yet."""
+    of original classes so a caller can restore them."""
     import ddsp.vocoder as ref_vocoder          # the reference checkout must be on sys.path
-    names = ("Sins", "CombSub", "CombSubSuperFast") + (("CombSubFast",) if experimental else ())
+    names = ("Sins", "CombSub", "CombSubSuperFast", "CombSubFast")
     saved = {name: getattr(ref_vocoder, name) for name in names}
     for name in names:
         setattr(ref_vocoder, name, getattr(vocoder, name))

@@ -19,8 +19,8 @@ _tables_lock = threading.Lock()
 
 
 def set_fir_impl(impl):
-    """'auto' / 'cuda' (CUDA-core kernel, the default), 'tc' (tcgen05 3xTF32 kernel, block size 512), 'cuda8' (older
-    scalar CUDA-core kernel) or 'fft' (FFT-domain kernel, experimental: not yet measured on hardware)."""
+    """'auto' (FFT-domain kernel for block size 512 and <= 1024 taps, else CUDA cores), 'cuda' (CUDA-core direct
+    form), 'tc' (tcgen05 3xTF32 kernel, block size 512), 'cuda8' (older scalar CUDA-core kernel) or 'fft'."""
     _lib.check(_lib.lib().b2d_set_fir_impl({"auto": 0, "cuda": 1, "tc": 2, "cuda8": 3, "fft": 4}[impl]), "b2d_set_fir_impl")
 
 
@@ -365,7 +365,7 @@ def set_sinegen_impl(name):
 
 def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utterance_offset=0):
     """CombSubFast after the source: comb [B, T] + raw controls [B, nF, block+1] -> signal [B, T]
-    (reference ddsp/vocoder.py:758-784).  EXPERIMENTAL: not yet validated on hardware."""
+    (reference ddsp/vocoder.py:758-784)."""
     _need_cuda_f32("comb", comb)
     B, T = comb.shape
     nF = T // block

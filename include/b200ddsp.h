@@ -97,7 +97,7 @@ int    b2d_ir_build(const float* c, int64_t ctrl_stride, int mode, const float* 
 /* ---------------------------------------------------------------------------------------
  * Linear time-varying FIR (frequency_filter's convolution).   replaces ddsp/core.py:120-182
  * (fft_convolve: Bartlett-windowed 50%-overlap frames, per-frame IR, overlap-add, crop
- * with delay L/2).  Computed in direct form:
+ * with delay L/2).  The linear convolution it defines is
  *   y[n] = sum_tau ((1-phi_m) h_f[tau] + phi_m h_{f+1}[tau]) x[m],  m = n + L/2 - tau,
  *   f = floor(m/P), phi_m = (m mod P)/P, h_{nF} := h_{nF-1}, x = 0 outside [0,T).
  * Up to two independent filters ("jobs") run in one launch and their outputs can be
@@ -113,15 +113,14 @@ int b2d_ltv_fir(const float* x1, const float* ir1, int taps1, float* y1,
                 float* mix, uint64_t seed, int64_t utterance_offset,
                 int B, int n_frames, int block, void* stream);
 
-/* Two implementations of the tiled kernel exist: CUDA cores (default; block size multiple of
- * 256) and tcgen05 tensor cores (3xTF32, block size 512; correct but operand-bandwidth bound and
- * ~3x slower on B200).  0 = automatic (CUDA cores), 1 = CUDA cores, 2 = tensor
- * cores, 3 = CUDA cores forcing the older 8-outputs-per-thread scalar-FFMA kernel (the default
- * CUDA-core kernel for block sizes that are multiples of 512 uses 16 outputs per thread and packed
- * fma.rn.f32x2), 4 = FFT-domain evaluation (ltv_fir_fft.cu: per input hop one 1024-point FFT per signal, the
- * impulse responses' spectra, and one inverse FFT per pair of hops, 2048 points above 512 taps; block size 512 and
- * <= 1024 taps, other shapes use the CUDA-core kernel; ~4x fewer instructions than the direct form.  EXPERIMENTAL: pinned by a CPU run of the
- * kernel source (tests/emu/), not yet measured on hardware, therefore not the default).
+/* Kernel selection for b2d_ltv_fir and the synthesizer drivers.  0 = automatic: the FFT-domain kernel
+ * (ltv_fir_fft.cu: per input hop one N-point FFT per signal, the impulse responses' spectra and one inverse FFT per
+ * pair of hops; N = 1024 up to 512 taps, 2048 up to 1024 taps; ~4x fewer instructions than the direct form,
+ * 0.37 ms against 1.18 ms on B200 for Sins' two 510-tap filters) when the block size is 512 and no filter has more than
+ * 1024 taps, otherwise the CUDA-core direct form (block size multiple of 256).  1 = CUDA-core direct form
+ * (16 outputs per thread, packed fma.rn.f32x2), 2 = tcgen05 tensor cores (3xTF32, block size 512; correct but
+ * operand-bandwidth bound and ~3x slower), 3 = the older 8-outputs-per-thread scalar-FFMA direct form,
+ * 4 = FFT-domain kernel wherever it applies.  B2D_FIR_AUTO=cuda in the environment makes 0 mean 1.
  * Process-wide test/diagnostic knob. */
 int b2d_set_fir_impl(int impl);
 
@@ -224,8 +223,7 @@ int b2d_source_module(const float* f0, const float* rand_ini, const float* noise
  * :743-751 = b2d_phase_scan); controls are raw Unit2Control outputs [B, n_frames, block+1] with a common frame
  * stride; noise_in [B, T] uniform(-1,1) or NULL = in-kernel Philox (same stream as b2d_ltv_fir).
  * Frames of 2*block at hop block, sqrt-Hann analysis and synthesis windows, filter row min(q, n_frames-1),
- * overlap-add cropped by block on both sides.  block must be 512.
- * STATUS: built and pinned by a CPU model of the kernel (tests/test_csfast_math.py); not yet run on hardware. */
+ * overlap-add cropped by block on both sides.  block must be 512. */
 int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude, const float* c_harmonic_phase,
                            const float* c_noise_magnitude, int64_t ctrl_stride, const float* noise_in,
                            uint64_t seed, int64_t utterance_offset, int B, int n_frames, int block,

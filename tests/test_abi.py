@@ -38,7 +38,11 @@ def test_argument_errors_do_not_touch_the_device(lib):
     assert lib.b2d_ir_build(16, 256, 7, 0, 16, 1, 1, 256, 44100.0, 16, 0) == -4             # unknown mode
     assert lib.b2d_ir_build(16, 256, 2, 0, 16, 1, 1, 256, 44100.0, 16, 0) == -1             # dynamic w/o f0
     assert lib.b2d_ltv_fir(16, 16, 510, 16, 0, 0, 0, 0, 0, 0, 0, 1, 1, 100, 0) == -4        # block % 256
+    assert lib.b2d_set_fir_impl(1) == 0                                                      # direct form only:
     assert lib.b2d_ltv_fir(16, 16, 510, 16, 16, 16, 1022, 16, 16, 0, 0, 1, 1, 512, 0) == -4  # unequal taps
+    assert lib.b2d_set_fir_impl(0) == 0                                                      # (the FFT kernel takes them)
+    assert lib.b2d_ltv_fir(16, 16, 511, 16, 0, 0, 0, 0, 0, 0, 0, 1, 1, 512, 0) == -2         # odd tap count
+    assert lib.b2d_set_fir_impl(5) == -4
     assert lib.b2d_ltv_fir(4, 16, 510, 16, 0, 0, 0, 0, 0, 0, 0, 1, 1, 512, 0) == -3         # misaligned x
     assert lib.b2d_sins_workspace_bytes(32, 861, 512, 256, 256) == 32 * 861 * 512 * 4 + 2 * 32 * 861 * 510 * 4
     assert lib.b2d_dft_tables_bytes(256) == 2 * 256 * 128 * 4 + 16 * 8 * 128 * 8 * 4   # CUDA-core tables + tensor-core image

@@ -75,7 +75,7 @@ def test_state_dict_round_trip_with_the_reference_classes(tmp_path):
         saved = pkg.patch_reference()
         try:
             assert V.Sins is pkg.Sins and V.CombSubSuperFast is pkg.CombSubSuperFast
-            assert V.CombSubFast is not pkg.CombSubFast            # experimental classes are opt-in
+            assert V.CombSubFast is pkg.CombSubFast
             import nsf_hifigan.models as nsf
             assert nsf.SineGen is pkg.SineGen and nsf.SourceModuleHnNSF is pkg.SourceModuleHnNSF
             model2, _ = V.load_model(str(tmp_path / "model_1.pt"), device="cpu")   # the REFERENCE's loader

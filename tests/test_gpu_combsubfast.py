@@ -1,10 +1,6 @@
 """GPU parity of the CombSubFast kernel against the live-reference goldens and the fp64 closed form.
 
-The kernel was written after the round's GPU budget was spent: it builds for sm_100a and its algorithm is pinned on
-the CPU (tests/test_csfast_math.py), but it has not executed on hardware yet.  These tests therefore only run when
-B2D_EXPERIMENTAL=1 is set (first GPU call of the next round); they are the acceptance gate for un-gating the module."""
-import os
-
+The same kernel source is also executed on the CPU by tests/emu/ (tests/test_emu_combsubfast.py)."""
 import numpy as np
 import pytest
 import torch
@@ -13,9 +9,7 @@ from ddsp_svc_b200 import CombSubFast, FixedControls, ops, synthetic as syn
 from tests import report, util
 from tests.golden import cases as G
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B2D_EXPERIMENTAL") != "1",
-                                 reason="CombSubFast kernel not yet validated on hardware (set B2D_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 SR, P = G.SR, G.P
 OFFICIAL_RMS, GATE_RMS = 1e-4, 2e-6

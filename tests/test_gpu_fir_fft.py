@@ -1,11 +1,8 @@
 """The FFT-domain time-varying FIR (csrc/ltv_fir_fft.cu, ops.set_fir_impl("fft")) against the CUDA-core kernel, the
 oracle and the goldens, including full Sins / CombSub forwards through it.
 
-Written after the round's GPU budget was spent: the kernel source is pinned on the CPU by tests/emu/ but has not run
-on hardware, so these tests only run with B2D_EXPERIMENTAL=1 (first GPU call of the next round).  If they pass and
-bench.py --fir-impl fft is faster, the kernel becomes the default dispatch for block size 512 / <= 512 taps."""
-import os
-
+It is the automatic dispatch for block size 512 and <= 1024 taps (0.37 ms against 1.18 ms on B200), so every Sins /
+CombSub test also runs through it; these tests compare it explicitly with the direct form."""
 import numpy as np
 import pytest
 import torch
@@ -14,9 +11,7 @@ from ddsp_svc_b200 import CombSub, FixedControls, Sins, ops, synthetic as syn
 from tests import report, util
 from tests.golden import cases as G
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B2D_EXPERIMENTAL") != "1",
-                                 reason="FFT-domain FIR not yet validated on hardware (set B2D_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 SR, P = G.SR, G.P
 
