@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(kTile) sinegen_kernel(SgParams p) {
 //     assembled with integer ops, rint() by the add-magic-constant trick: the SFU pipe only sees 4 MUFU per
 //     normal pair and one per sine;
 //   * frame lookup, f0/sr, rand_ini and the Linear weights once per thread instead of once per sample;
-//   * PACKED: the reference-ordered fp32 chain of two samples at a time in f32x2 instructions
-//     (mul/add/fma.rn.f32x2 round each lane exactly like the scalar ops, so parity is unchanged);
+//   * MODE 1 only: the fp32 chain of two samples at a time in f32x2 instructions.  NOT bit-compatible with the scalar
+//     chain: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (SASS: "FFMA2 R18, R46.F32x2, 2, R67.F32"), so
+//     theta = rad*(h+1) + rho is rounded once instead of twice (max output error 3e-6 vs 3e-8) -- kept as an option;
 //   * FUSED (SourceModuleHnNSF): no shared-memory tile at all, one 128-bit store of 4 merged samples.
 constexpr int kQ = 4;
 constexpr int kThreads4 = 128;
@@ -232,7 +233,7 @@ __device__ __forceinline__ float sin_turns(float theta) {
     return __sinf(r);
 }
 
-// MODE 0: scalar arithmetic; MODE 1: packed f32x2 arithmetic (default).  80 registers, 6 CTAs per SM.
+// MODE 0: scalar arithmetic (default); MODE 1: packed f32x2 arithmetic.  80 registers, 6 CTAs per SM.
 // Measured dead ends (B200, 64 x 10 s x 9): compiling for 8 CTAs/SM (64 registers) 0.357 vs 0.345 ms -- the
 // kernel is bound by the issue slots / pipe mix, not by latency; a streaming variant (one Philox block -> 4
 // outputs -> one 128-bit shared store, 48 registers) 0.42 ms, 320 M vs 248 M warp instructions.
@@ -455,7 +456,10 @@ static int sinegen_launch(const float* f0, const float* rand_ini, const float* n
     p.seed = seed; p.utt_off = utterance_offset;
     p.lin_w = lin_w; p.lin_b = lin_b; p.merged = merged;
     const long long T = (long long)n_frames * upp;
-    const int impl = g_sinegen_impl == 0 ? 3 : g_sinegen_impl;
+    // auto = the scalar 4-samples-per-thread kernel: the packed variant is ~3-5 % faster, but ptxas contracts its
+    // mul.rn.f32x2 + add.rn.f32x2 pairs into FFMA2 (one rounding instead of the reference's two), which moves the sine
+    // argument by an ulp: max error 3e-6 instead of 3e-8 against the reference (still inside the 2e-6 RMS gate)
+    const int impl = g_sinegen_impl == 0 ? 2 : g_sinegen_impl;
     if (impl >= 2 && (dim == 9 || dim == 1)) {
         if (dim == 9) launch_v2<9>(p, B, T, impl, st);
         else launch_v2<1>(p, B, T, impl, st);

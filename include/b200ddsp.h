@@ -230,8 +230,9 @@ int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude,
                            float* signal, void* stream);
 
 /* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto, 1 one sample per
- * thread (round-1 kernel; also the only one for dim other than 1 or 9), 2 four samples per thread,
- * 3 four samples per thread with packed f32x2 arithmetic (auto).  Impl 1 and 2/3 draw DIFFERENT in-kernel
+ * thread (first kernel of round 1; also the only one for dim other than 1 or 9), 2 four samples per thread (auto),
+ * 3 four samples per thread with packed f32x2 arithmetic (3-5 % faster, but ptxas fuses its packed mul+add pairs, so
+ * the sine argument is rounded once instead of twice: max error 3e-6 instead of 3e-8).  Impl 1 and 2/3 draw DIFFERENT in-kernel
  * noise streams (both Philox4x32-10 keyed by seed / global utterance / position). */
 int b2d_set_sinegen_impl(int impl);
 
