@@ -34,6 +34,8 @@ WORKLOADS = {
                     label="CombSub (old) forward DSP, B=32 x 10 s, n_mag 256/512/256 (BASELINE configs[2], class CombSub)"),
     "superfast": dict(kind="superfast", B=32, sec=10, win=2048,
                       label="CombSubSuperFast forward DSP (configs/combsub.yaml), B=32 x 10 s, win 2048 (BASELINE configs[2])"),
+    "combsubfast": dict(kind="combsubfast", B=32, sec=10,
+                        label="CombSubFast forward DSP (the variant diffusion / reflow embed), B=32 x 10 s, 1024-point sqrt-Hann frames"),
     "sinegen": dict(kind="sinegen", B=64, sec=10, dim=9,
                     label="nsf_hifigan SineGen, B=64 x 10 s, 9 harmonics (BASELINE configs[4])"),
     "srcmod": dict(kind="srcmod", B=64, sec=10, dim=9,
@@ -53,6 +55,8 @@ def algorithmic_bytes(w, nF):
         return 4 * B * nF * (1 + c) + 4 * B * T * 3
     if w["kind"] == "superfast":
         return 4 * B * nF * (1 + 4 * (w["win"] // 2 + 1)) + 4 * B * T
+    if w["kind"] == "combsubfast":
+        return 4 * B * nF * (1 + 3 * (P + 1)) + 4 * B * T
     if w["kind"] == "sinegen":
         return 4 * B * nF + 4 * B * T * w["dim"]
     if w["kind"] == "srcmod":
@@ -69,6 +73,8 @@ def split_map_of(w):
         return syn.combsub_split_map(w["Ma"], w["Mh"], w["Mn"])
     if k == "superfast":
         return syn.superfast_split_map(w["win"])
+    if k == "combsubfast":
+        return syn.combsubfast_split_map(P)
     return None
 
 
@@ -82,6 +88,8 @@ def oracle_forward(w, f0, ctrls):
         return tp.combsub_forward(f0, ctrls, SR, P)
     if k == "superfast":
         return tp.superfast_forward(f0, ctrls, SR, P, w["win"])
+    if k == "combsubfast":
+        return tp.combsubfast_forward(f0, ctrls, SR, P)
     if k == "srcmod":
         import torch
         g = torch.Generator().manual_seed(5)
@@ -250,8 +258,8 @@ class Runner:
     """Per-workload device state: how to run one step and how to time each kernel alone."""
 
     def __init__(self, w, dev, rank, torch):
-        from ddsp_svc_b200 import (CombSub, CombSubSuperFast, FixedControls, SineGen, SourceModuleHnNSF, Sins, ops,
-                                   synthetic as syn)
+        from ddsp_svc_b200 import (CombSub, CombSubFast, CombSubSuperFast, FixedControls, SineGen, SourceModuleHnNSF,
+                                   Sins, ops, synthetic as syn)
         self.w, self.dev, self.rank, self.torch, self.ops, self.syn = w, dev, rank, torch, ops, syn
         B = self.B = w["B"]
         nF = self.nF = syn.n_frames_for(w["sec"], SR, P)
@@ -280,6 +288,8 @@ class Runner:
             self.model = Sins(SR, P, w["H"], w["Ma"], w["Mn"], unit2ctrl=self.fixed).to(dev)
         elif k == "combsub":
             self.model = CombSub(SR, P, w["Ma"], w["Mh"], w["Mn"], unit2ctrl=self.fixed).to(dev)
+        elif k == "combsubfast":
+            self.model = CombSubFast(SR, P, unit2ctrl=self.fixed).to(dev)
         else:
             self.model = CombSubSuperFast(SR, P, w["win"], unit2ctrl=self.fixed).to(dev)
         self.out_h = torch.empty(B, self.T, dtype=torch.float32).pin_memory()
@@ -343,6 +353,13 @@ class Runner:
             lw, lb = self.model.l_linear.weight, float(self.model.l_linear.bias)
             return {"source_module(scan+stream)": lambda: ops.source_module(f0[..., 0], P, SR, w["dim"], self.rand_ini,
                                                                             lw, lb, seed=1)}
+        if k == "combsubfast":
+            fp, _ = ops.phase_scan(f0, P, SR)
+            comb = ops.comb_source(f0, fp, P, SR)
+            return {"phase_scan": lambda: ops.phase_scan(f0, P, SR),
+                    "comb_source": lambda: ops.comb_source(f0, fp, P, SR),
+                    "combsubfast_kernel": lambda: ops.combsubfast_filter(comb, c["harmonic_magnitude"], c["harmonic_phase"],
+                                                                         c["noise_magnitude"], P, seed=1)}
         if k == "superfast":
             ws, _ = ops.superfast_scan(f0, P, SR)
             return {"superfast_scan": lambda: ops.superfast_scan(f0, P, SR),

@@ -18,6 +18,24 @@ def test_algorithmic_bytes_match_the_survey():
     assert abs(per("superfast") - 36.039) < 2e-3
     assert abs(per("combsub") - 20.008) < 2e-3
     assert abs(per("sinegen") - 36.008) < 2e-3
+    assert abs(per("srcmod") - 4.008) < 2e-3           # fused tanh(Linear(9 -> 1)): one value per sample
+    assert abs(per("combsubfast") - 16.031) < 2e-3     # 3 x 513 control words per frame + 1 output
+
+
+def test_cpu_arm_runs_every_workload_kind():
+    """the oracle port behind --impl reference / cpu_baseline accepts every workload (tiny sizes)"""
+    import torch
+    from ddsp_svc_b200 import synthetic as syn
+    for name, w in bench.WORKLOADS.items():
+        w = dict(w, B=1, sec=0.05)
+        nF = max(2, syn.n_frames_for(w["sec"], bench.SR, bench.P))
+        sm = bench.split_map_of(w)
+        f0 = syn.make_f0(1, nF, bench.SR, bench.P)
+        ctrls = syn.make_ctrl(1, nF, sm)[1] if sm else None
+        with torch.no_grad():
+            out = bench.oracle_forward(w, f0, ctrls)
+        key = "signal" if "signal" in out else "out"
+        assert out[key].shape[1] == nF * bench.P, name
 
 
 def test_reference_arm_prints_the_contract_line():
