@@ -415,6 +415,8 @@ def main():
                          "for 4 equal chunks on the Sins workload)")
     ap.add_argument("--fir-impl", default="auto", choices=["auto", "cuda", "tc", "cuda8", "fft"],
                     help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
+    ap.add_argument("--fft-arith", default="scalar", choices=["scalar", "packed"],
+                    help="A/B switch: packed f32x2 complex additions in the FFT kernels (ops.set_fft_arith)")
     ap.add_argument("--sinegen-impl", default="auto", choices=["auto", "v1", "v2", "v2p"],
                     help="A/B switch for the SineGen / source-module kernel (ops.set_sinegen_impl)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
@@ -445,6 +447,8 @@ def main():
         run.ops.set_sinegen_impl(args.sinegen_impl)
     if args.fir_impl != "auto":
         run.ops.set_fir_impl(args.fir_impl)
+    if args.fft_arith != "scalar":
+        run.ops.set_fft_arith(args.fft_arith)
     B, nF, T = run.B, run.nF, run.T
     do_gather = world > 1 and not args.no_gather
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2

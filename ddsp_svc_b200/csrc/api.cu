@@ -28,6 +28,14 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 }  // namespace b2d
 
+namespace b2d { bool g_fft_packed = false; }
+
+extern "C" int b2d_set_fft_arith(int packed) {
+    if (packed != 0 && packed != 1) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fft_arith: %d not in {0, 1}", packed);
+    b2d::g_fft_packed = packed != 0;
+    return 0;
+}
+
 extern "C" int b2d_version(void) { return B2D_VERSION; }
 extern "C" const char* b2d_last_error(void) { return b2d::err_buf(); }
 

@@ -21,6 +21,8 @@ inline int check_launch(const char* what) {
     return 0;
 }
 
+// b2d_set_fft_arith(1): the FFT kernels (ltv_fir_fft, superfast, combsubfast) use packed f32x2 complex additions
+extern bool g_fft_packed;
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace b2d

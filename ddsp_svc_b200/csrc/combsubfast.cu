@@ -60,6 +60,8 @@ __device__ __forceinline__ BinFilter make_filter(float hm, float hp, float nm) {
 constexpr size_t kSmemBytes = (size_t)2 * kPad * sizeof(float2) + (size_t)(kTw2 + kTw3) * sizeof(float2) +
                               (size_t)kN * sizeof(float);      // 17408 + 1920 + 4096 = 23424 B
 
+// PK: complex additions as packed f32x2 instructions (fft_regs.cuh Ar<true>)
+template <bool PK>
 __global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);          // frame a: time -> spectrum -> pair spectrum -> pair time
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
             for (int i = tid; i < kPad; i += kThreads) bufB[i] = make_float2(0.f, 0.f);
         }
         __syncthreads();
-        fft1024<2>(bufA, tw2, tw3, tid);
+        b2d_fft_smem::fft_forward<1024, 2, PK>(bufA, tw2, tw3, tid);
 
         // ---- separate, filter, pair: Y = Sa + j Sb (Hermitian extension), stored re/im-swapped in bufA ----
 #pragma unroll
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
         __syncthreads();
 
         // ---- inverse of the pair: ifft(Y) = swap(fft(swap(Y))) / N ----
-        fft1024<1>(bufA, tw2, tw3, tid);
+        b2d_fft_smem::fft_forward<1024, 1, PK>(bufA, tw2, tw3, tid);
 
         // ---- window, overlap-add, store: frame a = stored .y, frame b = stored .x ----
         const int i0 = tid << 2;
@@ -225,7 +227,8 @@ extern "C" int b2d_combsubfast_filter(const float* comb, const float* c_harmonic
     p.ctrl_stride = ctrl_stride; p.out = signal; p.nF = n_frames; p.G = 32;
     p.seed = seed; p.utt_off = utterance_offset;
     const dim3 grid((unsigned)((n_frames + p.G - 1) / p.G), B);
-    combsubfast_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    if (b2d::g_fft_packed) combsubfast_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    else combsubfast_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
     return b2d::check_launch("combsubfast");
 }
 #endif  // B2D_HOST_EMU

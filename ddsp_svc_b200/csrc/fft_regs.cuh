@@ -14,13 +14,38 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }  // a * (-j)
 
+// Complex add / subtract policy.  PK = false: two scalar FADDs.  PK = true: one packed add.rn.f32x2 / sub.rn.f32x2
+// (SASS FADD2; a float2 that comes from a 64-bit shared-memory load is already an aligned register pair, so the
+// mov.b64 pack / unpack disappear).  Identical results (per-lane IEEE add); half the issue slots for the ~2/3 of an
+// FFT's instructions that are butterfly additions.
+template <bool PK> struct Ar {
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return cadd(a, b); }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return csub(a, b); }
+};
+#ifndef B2D_HOST_EMU
+template <> struct Ar<true> {
+    static __device__ __forceinline__ unsigned long long pk(float2 a) {
+        unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r;
+    }
+    static __device__ __forceinline__ float2 upk(unsigned long long v) {
+        float2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(v)); return a;
+    }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) {
+        unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d);
+    }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b) {
+        unsigned long long d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d);
+    }
+};
+#endif
+
 // forward DFT of 2^n points, natural order in and out (recursive decimation in time, unrolled)
-template <int R> struct Dft;
-template <> struct Dft<1> { static __device__ __forceinline__ void run(float2*) {} };
-template <> struct Dft<2> {
+template <int R, bool PK = false> struct Dft;
+template <bool PK> struct Dft<1, PK> { static __device__ __forceinline__ void run(float2*) {} };
+template <bool PK> struct Dft<2, PK> {
     static __device__ __forceinline__ void run(float2* v) {
         const float2 a = v[0], b = v[1];
-        v[0] = cadd(a, b); v[1] = csub(a, b);
+        v[0] = Ar<PK>::add(a, b); v[1] = Ar<PK>::sub(a, b);
     }
 };
 template <int R, int K> __device__ __forceinline__ float2 twid(float2 o) {  // o * exp(-2 pi i K / R)
@@ -34,23 +59,23 @@ template <int R, int K> __device__ __forceinline__ float2 twid(float2 o) {  // o
     const float s = (K == 1) ? s1 : (K == 3) ? c1 : (K == 5) ? c1 : s1;
     return make_float2(fmaf(o.x, c, o.y * s), fmaf(o.y, c, -o.x * s));  // (c - j s) * o
 }
-template <int R, int K> struct Comb {
+template <int R, int K, bool PK> struct Comb {
     static __device__ __forceinline__ void run(const float2* e, const float2* o, float2* v) {
         const float2 t = twid<R, K>(o[K]);
-        v[K] = cadd(e[K], t);
-        v[K + R / 2] = csub(e[K], t);
-        Comb<R, K + 1>::run(e, o, v);
+        v[K] = Ar<PK>::add(e[K], t);
+        v[K + R / 2] = Ar<PK>::sub(e[K], t);
+        Comb<R, K + 1, PK>::run(e, o, v);
     }
 };
-template <int R> struct Comb<R, R / 2> { static __device__ __forceinline__ void run(const float2*, const float2*, float2*) {} };
-template <int R> struct Dft {
+template <int R, bool PK> struct Comb<R, R / 2, PK> { static __device__ __forceinline__ void run(const float2*, const float2*, float2*) {} };
+template <int R, bool PK> struct Dft {
     static __device__ __forceinline__ void run(float2* v) {
         float2 e[R / 2], o[R / 2];
 #pragma unroll
         for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
-        Dft<R / 2>::run(e);
-        Dft<R / 2>::run(o);
-        Comb<R, 0>::run(e, o, v);
+        Dft<R / 2, PK>::run(e);
+        Dft<R / 2, PK>::run(o);
+        Comb<R, 0, PK>::run(e, o, v);
     }
 };
 

@@ -30,7 +30,7 @@ template <int N> struct Plan {
 // thread otherwise.  A stage reads, hits a barrier, then writes; different stages touch different transforms, so stage
 // s+1 may start reading while other threads still write stage s, and only one stage's butterflies are live per thread.
 // Barriers per pass: stages + 1.
-template <int N, int R, int NS, int TW, int NBATCH>
+template <int N, int R, int NS, int TW, int NBATCH, bool PK = false>
 __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__ tw, int tid) {
     constexpr int NB = N / R;                                        // butterflies per FFT
     constexpr int PER = NB > kThreads ? NB / kThreads : 1;           // butterflies per thread and stage
@@ -63,7 +63,7 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
                     v[u][4] = cmul(v[u][4], w4); v[u][5] = cmul(v[u][5], w5); v[u][6] = cmul(v[u][6], w6);
                     v[u][7] = cmul(v[u][7], w7);
                 }
-                Dft<R>::run(v[u]);
+                Dft<R, PK>::run(v[u]);
             }
         }
         __syncthreads();
@@ -82,12 +82,12 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
 }
 
 // forward FFT of NBATCH transforms at buf, buf + kPad, ...
-template <int N, int NBATCH>
+template <int N, int NBATCH, bool PK = false>
 __device__ __forceinline__ void fft_forward(float2* buf, const float2* tw2, const float2* tw3, int tid) {
     constexpr int R2 = Plan<N>::kR2;
-    fft_pass<N, 16, 1, 0, NBATCH>(buf, nullptr, tid);
-    fft_pass<N, R2, 16, 1, NBATCH>(buf, tw2, tid);
-    fft_pass<N, 8, 16 * R2, 2, NBATCH>(buf, tw3, tid);
+    fft_pass<N, 16, 1, 0, NBATCH, PK>(buf, nullptr, tid);
+    fft_pass<N, R2, 16, 1, NBATCH, PK>(buf, tw2, tid);
+    fft_pass<N, 8, 16 * R2, 2, NBATCH, PK>(buf, tw3, tid);
 }
 
 // twiddle tables of passes 2 and 3 (call with all threads, then __syncthreads)

@@ -64,7 +64,8 @@ __device__ __forceinline__ void split2(float2 zk, float2 zm, float2& A, float2& 
     C = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
 }
 
-template <int N, int NJ>
+// PK: complex additions as packed f32x2 instructions (fft_regs.cuh Ar<true>): same results, fewer issue slots
+template <int N, int NJ, bool PK>
 __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_fir_fft_kernel(FftFirParams p) {
     constexpr int kN = N, kPad = Plan<N>::kPad, kTw2 = Plan<N>::kTw2, kTw3 = Plan<N>::kTw3;
     constexpr int kBins = N / 2 / kThreads;          // bins k = tid + 128 u per thread (DC.. N/2-1); Nyquist on thread 0
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
 #pragma unroll
     for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs, gs, false);
     __syncthreads();
-    fft_forward<N, NJ>(F + 2 * NJ * kPad, tw2, tw3, tid);
+    fft_forward<N, NJ, PK>(F + 2 * NJ * kPad, tw2, tw3, tid);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const float2* H = F + (2 * NJ + j) * kPad;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
             load_ir_pair(j, g + 1, g + 2, true);
         }
         __syncthreads();
-        fft_forward<N, 3 * NJ>(F, tw2, tw3, tid);
+        fft_forward<N, 3 * NJ, PK>(F, tw2, tw3, tid);
 
         // ---- Y_g = X_g H_g + XU_g (H_{g+1} - H_g),  Y_{g+1} = X_{g+1} H_{g+1} + XU_{g+1} (H_{g+2} - H_{g+1});
         //      paired as Y_g + j Y_{g+1} (Hermitian extension), stored re/im-swapped over XA(j) ----
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
                 split2(XA[ik], XA[im], Xa, XUa);
                 split2(XB[ik], XB[im], Xb, XUb);
                 split2(HH[ik], HH[im], Ha, Hb);
-                const float2 ya = cadd(cmul(Xa, Hp[j][u]), cmul(XUa, csub(Ha, Hp[j][u])));
-                const float2 yb = cadd(cmul(Xb, Ha), cmul(XUb, csub(Hb, Ha)));
+                const float2 ya = Ar<PK>::add(cmul(Xa, Hp[j][u]), cmul(XUa, Ar<PK>::sub(Ha, Hp[j][u])));
+                const float2 yb = Ar<PK>::add(cmul(Xb, Ha), cmul(XUb, Ar<PK>::sub(Hb, Ha)));
                 // Y[k] = ya + j yb;  Y[N-k] = conj(ya) + j conj(yb);  stored as (im, re)
                 XA[ik] = make_float2(ya.y + yb.x, ya.x - yb.y);
                 XA[im] = make_float2(yb.x - ya.y, ya.x + yb.y);
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
         __syncthreads();
 
         // ---- inverse of the pairs (batch over jobs): hop g = stored .y / N, hop g+1 = stored .x / N ----
-        fft_forward<N, NJ>(F, tw2, tw3, tid);
+        fft_forward<N, NJ, PK>(F, tw2, tw3, tid);
 
         // ---- overlap-add at the delay-compensated positions t = gP - L/2 + n (hop g) and + P (hop g+1), kept to this
         //      CTA's hops.  Slots hit twice (n and n - P) belong to the same thread: no race. ----
@@ -257,20 +258,25 @@ bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs) {
     return P == kHop && taps1 > 0 && (njobs == 1 || taps2 > 0) && tmax <= 1024;
 }
 
-template <int N, int NJ>
-static int launch_fir_fft(const FftFirParams& p, dim3 grid, cudaStream_t st) {
+template <int N, int NJ, bool PK>
+static int launch_fir_fft_as(const FftFirParams& p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = fir_fft_smem<N, NJ>();
     static bool attr_set = false;
     if (!attr_set) {
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
         }
-        cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
-    ltv_fir_fft_kernel<N, NJ><<<grid, kThreads, smem, st>>>(p);
+    ltv_fir_fft_kernel<N, NJ, PK><<<grid, kThreads, smem, st>>>(p);
     return check_launch("ltv_fir(fft)");
+}
+
+template <int N, int NJ>
+static int launch_fir_fft(const FftFirParams& p, dim3 grid, cudaStream_t st) {
+    return g_fft_packed ? launch_fir_fft_as<N, NJ, true>(p, grid, st) : launch_fir_fft_as<N, NJ, false>(p, grid, st);
 }
 
 int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,

@@ -94,7 +94,7 @@ using namespace b2d_fft;   // cadd / csub / cmul / Dft<R>: register DFTs shared 
 //   reads : padi(j + r N/R)           = padi(j) + r (N/R + N/R/16)
 //   writes: NS = 1   -> 17 j + r ;  NS = 16 -> (j/16) 272 + j%16 + 17 r ;  NS = 256 -> padi(j) + 272 r
 // TW: 0 none (first pass), 1 full table [R-1][NS], 2 powers of tw[k] (= exp(-2 pi i k / (NS R)))
-template <int R, int NS, int TW>
+template <int R, int NS, int TW, bool PK>
 __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__ tw, int tid) {
     constexpr int NB = kN / R;               // butterflies
     constexpr int PER = NB / kThreads;       // per thread (1 for R=16, 2 for R=8)
@@ -120,7 +120,7 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
                 v[u][5] = cmul(v[u][5], w5); v[u][6] = cmul(v[u][6], w6); v[u][7] = cmul(v[u][7], w7);
             }
         }
-        Dft<R>::run(v[u]);
+        Dft<R, PK>::run(v[u]);
     }
     __syncthreads();
 #pragma unroll
@@ -137,10 +137,11 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
     __syncthreads();
 }
 
+template <bool PK>
 __device__ __forceinline__ void fft2048(float2* buf, const float2* tw2, const float2* tw3, int tid) {
-    fft_pass<16, 1, 0>(buf, nullptr, tid);
-    fft_pass<16, 16, 1>(buf, tw2, tid);
-    fft_pass<8, 256, 2>(buf, tw3, tid);
+    fft_pass<16, 1, 0, PK>(buf, nullptr, tid);
+    fft_pass<16, 16, 1, PK>(buf, tw2, tid);
+    fft_pass<8, 256, 2, PK>(buf, tw3, tid);
 }
 
 struct SfParams {
@@ -206,6 +207,8 @@ constexpr size_t kSmemBytes = (size_t)2 * kPadN * sizeof(float2) + (size_t)kN * 
                               (size_t)kRingHops * kHop * sizeof(float) + (size_t)kWinLen * sizeof(float) +
                               (size_t)(15 * 16 + 256) * sizeof(float2);
 
+// PK: complex additions of the FFT butterflies as packed f32x2 instructions (fft_regs.cuh Ar<true>)
+template <bool PK>
 __global__ void __launch_bounds__(kThreads, 3) superfast_kernel(SfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);          // [kPadN] frame time/frequency data
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 3) superfast_kernel(SfParams p) {
                 cnm[8] = __ldg(p.c_nm + crow + kHalf); cnp[8] = __ldg(p.c_np + crow + kHalf);
             }
             __syncthreads();
-            fft2048(bufA, tw2, tw3, tid);
+            fft2048<PK>(bufA, tw2, tw3, tid);
             // ---- split comb/noise spectra, apply the filters, accumulate the pair spectrum ----
 #pragma unroll
             for (int it = 0; it < 9; ++it) {
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 3) superfast_kernel(SfParams p) {
             __syncthreads();
         }
         // ---- inverse transform of the pair, windowed overlap-add into the ring ----
-        fft2048(bufS, tw2, tw3, tid);
+        fft2048<PK>(bufS, tw2, tw3, tid);
         const float inv_n = 1.0f / (float)kN;
         int hslot[5];       // ring slot (x512) of hops qa-2 .. qa+2
 #pragma unroll
@@ -445,9 +448,14 @@ extern "C" int b2d_superfast_synth(const void* workspace, const float* c_harmoni
     p.G = G;
     p.seed = seed; p.utt_off = utterance_offset;
     const size_t smem = kSmemBytes;
-    cudaError_t e = cudaFuncSetAttribute(superfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return b2d::fail((int)e, "superfast_synth: smem attr: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(superfast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    superfast_kernel<<<dim3((n_frames + G - 1) / G, B), kThreads, smem, (cudaStream_t)stream>>>(p);
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return b2d::fail((int)e, "superfast_synth: smem attr: %s", cudaGetErrorString(e));
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        kern<<<dim3((n_frames + G - 1) / G, B), kThreads, smem, (cudaStream_t)stream>>>(p);
+        return 0;
+    };
+    const int rc = b2d::g_fft_packed ? go(superfast_kernel<true>) : go(superfast_kernel<false>);
+    if (rc) return rc;
     return b2d::check_launch("superfast_synth");
 }

@@ -384,3 +384,8 @@ def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utt
     _lib.check(rc, "b2d_combsubfast_filter")
     _count(1)
     return signal
+
+
+def set_fft_arith(name):
+    """'scalar' (default) | 'packed' (f32x2 complex additions in the FFT kernels; experimental, not yet run on hardware)."""
+    _lib.check(_lib.lib().b2d_set_fft_arith({"scalar": 0, "packed": 1}[name]), "b2d_set_fft_arith")

@@ -229,6 +229,12 @@ int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude,
                            uint64_t seed, int64_t utterance_offset, int B, int n_frames, int block,
                            float* signal, void* stream);
 
+/* Arithmetic of the shared-memory FFT kernels (ltv_fir_fft, superfast, combsubfast): 0 = scalar complex additions
+ * (default), 1 = packed add/sub.rn.f32x2 (one FADD2 per complex addition: identical results per lane, 15 % / 7 % fewer
+ * instructions in the FIR / SuperFast main loops by SASS count).  EXPERIMENTAL: builds, not yet run on hardware.
+ * Process-wide test/diagnostic knob. */
+int b2d_set_fft_arith(int packed);
+
 /* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto, 1 one sample per
  * thread (first kernel of round 1; also the only one for dim other than 1 or 9), 2 four samples per thread (auto),
  * 3 four samples per thread with packed f32x2 arithmetic (3-5 % faster, but ptxas fuses its packed mul+add pairs, so

@@ -12,6 +12,6 @@ extern "C" int emu_combsubfast(const float* comb, const float* hm, const float* 
     CfParams p;
     p.comb = comb; p.noise_in = noise_in; p.c_hm = hm; p.c_hp = hp; p.c_nm = nm; p.ctrl_stride = stride;
     p.out = out; p.nF = nF; p.G = G; p.seed = seed; p.utt_off = utt_off;
-    emu::launch((unsigned)((nF + G - 1) / G), (unsigned)B, kThreads, [&] { combsubfast_kernel(p); });
+    emu::launch((unsigned)((nF + G - 1) / G), (unsigned)B, kThreads, [&] { combsubfast_kernel<false>(p); });
     return 0;
 }

@@ -17,11 +17,11 @@ extern "C" int emu_ltv_fir_fft(const float* x1, const float* ir1, int L1, float*
     const int tmax = ir2 ? (L1 > L2 ? L1 : L2) : L1;
     if (tmax > 1024) return -4;
     if (tmax <= 512) {             // same size selection as b2d::ltv_fir_fft_launch
-        if (ir2) emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<1024, 2>(p); });
-        else emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<1024, 1>(p); });
+        if (ir2) emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<1024, 2, false>(p); });
+        else emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<1024, 1, false>(p); });
     } else {
-        if (ir2) emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<2048, 2>(p); });
-        else emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<2048, 1>(p); });
+        if (ir2) emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<2048, 2, false>(p); });
+        else emu::launch(gx, (unsigned)B, kThreads, [&] { ltv_fir_fft_kernel<2048, 1, false>(p); });
     }
     return 0;
 }
