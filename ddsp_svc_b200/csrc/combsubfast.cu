@@ -224,7 +224,10 @@ extern "C" int b2d_combsubfast_filter(const float* comb, const float* c_harmonic
     CfParams p;
     p.comb = comb; p.noise_in = noise_in;
     p.c_hm = c_harmonic_magnitude; p.c_hp = c_harmonic_phase; p.c_nm = c_noise_magnitude;
-    p.ctrl_stride = ctrl_stride; p.out = signal; p.nF = n_frames; p.G = 32;
+    p.ctrl_stride = ctrl_stride; p.out = signal; p.nF = n_frames;
+    int G = 32;            // hops per CTA: shorter chunks when the launch would not fill the GPU (cf. ltv_fir_fft.cu)
+    while (G > 2 && (long long)B * ((n_frames + G - 1) / G) < 148LL * 2) G >>= 1;
+    p.G = G;
     p.seed = seed; p.utt_off = utterance_offset;
     const dim3 grid((unsigned)((n_frames + p.G - 1) / p.G), B);
     if (b2d::g_fft_packed) combsubfast_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);

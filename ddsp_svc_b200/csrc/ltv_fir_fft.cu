@@ -288,7 +288,14 @@ int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, 
     FftFirParams p;
     p.job[0] = {x1, ir1, y1, taps1};
     p.job[1] = {x2, ir2, y2, njobs == 2 ? taps2 : taps1};
-    p.addend = addend; p.mix = mix; p.seed = seed; p.utt_off = utt_off; p.nF = nF; p.G = 32;
+    p.addend = addend; p.mix = mix; p.seed = seed; p.utt_off = utt_off; p.nF = nF;
+    // Hops per CTA.  A CTA walks its G + 2 input hops serially (~5.5 us per hop), so G = 32 is right when the grid fills
+    // the GPU (B = 32 x 10 s: 864 CTAs for 444 resident slots) but makes small launches -- one utterance of a real-time
+    // caller, one chunk of the host pipeline -- latency-bound; halve G (25 % / 50 % / 100 % recomputation at 8 / 4 / 2)
+    // until there are at least two CTAs per SM.
+    int G = 32;
+    while (G > 2 && (long long)B * ((nF + G - 1) / G) < 148LL * 2) G >>= 1;
+    p.G = G;
     const dim3 grid((unsigned)((nF + p.G - 1) / p.G), B);
     const int tmax = njobs == 2 ? (taps1 > taps2 ? taps1 : taps2) : taps1;
     if (tmax <= kHop) return njobs == 2 ? launch_fir_fft<1024, 2>(p, grid, st) : launch_fir_fft<1024, 1>(p, grid, st);

@@ -64,7 +64,7 @@ def _comb_fp32(name_or_inputs):
 
 
 @pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "combsubfast"])
-@pytest.mark.parametrize("hops", [32, 5, 1])
+@pytest.mark.parametrize("hops", [32, 16, 8, 5, 4, 2, 1])
 def test_kernel_source_matches_reference_golden(emu, name, hops):
     inp = G.build_inputs(name)
     gold = util.load_golden(name)

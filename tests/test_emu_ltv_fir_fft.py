@@ -63,7 +63,7 @@ def _case(B, nF, L, seed):
     return x, ir
 
 
-@pytest.mark.parametrize("nF,hops", [(1, 32), (2, 32), (3, 32), (7, 3), (7, 2), (7, 1), (40, 32), (33, 32), (34, 32)])
+@pytest.mark.parametrize("nF,hops", [(1, 32), (2, 32), (3, 32), (7, 3), (7, 2), (7, 1), (40, 32), (33, 32), (34, 32), (40, 16), (21, 8), (9, 4)])
 def test_one_job_matches_closed_form(emu, nF, hops):
     x, ir = _case(2, nF, 510, nF)
     out = emu(x, ir, hops=hops, want=("y1", "mix"))
