@@ -8,8 +8,8 @@
 //
 // Design (B200).  HBM traffic: 3 x 513 control values per frame = 12 B per output sample, + 4 B comb in and 4 B
 // out; everything else stays on chip.  23.4 KB shared memory, 128 registers -> 4 CTAs per SM.
-//  * one CTA owns G consecutive hops of one utterance and walks the G+1 frames that touch them, TWO frames
-//    per iteration;
+//  * one CTA owns G consecutive hops (G even) of one utterance and walks the G+1 frames that touch them plus the one
+//    that completes the last pair, TWO frames per iteration;
 //  * per frame one complex 1024-point FFT carries w*(comb + j*noise); both frames of the pair run as a batch
 //    through the same three Stockham passes (radix 16, 8, 8), so every pass has >= 128 butterflies for the
 //    128 threads;
@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
 
 #pragma unroll 1
     for (int q = h0; q <= h1; q += 2) {
-        const bool has_b = q + 1 <= h1;
+        // frames are always transformed in the same pairs (2m, 2m+1) (G is even): the chunk's last frame h1 is paired with
+        // h1 + 1 even though only its first half is used here, so that its round-off does not depend on the chunking and
+        // every output sample is bit-identical for any G / batch split.  Frame nF is the last one that exists.
+        const bool has_b = q + 1 <= nF;
         const int row_a = min(q, nF - 1), row_b = min(q + 1, nF - 1);            // frame nF reuses row nF-1 (:759,761)
         // ---- controls of both frames for this thread's bins k = tid + 128 u (and k = 0 / 512 on thread 0),
         //      issued before the FFT so their latency hides behind it ----
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
         if (have_tail)                                                            // hop q-1 = tail(q-1) + head(q)
             b2d::st_global_v4(out_row + (size_t)(q - 1) * kP + i0,
                               make_float4(tail[0] + head_a[0], tail[1] + head_a[1], tail[2] + head_a[2], tail[3] + head_a[3]));
-        if (has_b) {                                                              // hop q = second(q) + head(q+1)
+        if (has_b && q < h1) {                                                    // hop q = second(q) + head(q+1)
             b2d::st_global_v4(out_row + (size_t)q * kP + i0,
                               make_float4(second_a[0] + head_b[0], second_a[1] + head_b[1], second_a[2] + head_b[2],
                                           second_a[3] + head_b[3]));

@@ -19,8 +19,9 @@
 //     a hop is complete once the segment of the FOLLOWING input hop has been added and is then written exactly once
 //     (y1, y2 and mix = y1 + y2 (+ addend)) with 128-bit stores -- deterministic, no atomics.
 // 4 FFT-1024 per hop and job pair replace 2 x 2 x L x P = 1.04 M FMAs of the direct form (L = 510): ~4x fewer
-// instructions.  A CTA owns G hops of one utterance and processes the G+2 input hops that reach them; white-noise
-// input (x2 == nullptr) is the same Philox stream as in the direct-form kernels.
+// instructions.  A CTA owns G hops (G even) of one utterance and processes the G+2 input hops that reach them plus the
+// two that complete their pairs; white-noise input (x2 == nullptr) is the same Philox stream as in the direct-form
+// kernels.
 //
 // Measured on B200 (Sins, B = 32 x 10 s, two 510-tap filters): 0.372 ms against 1.18 ms for the direct form -> this is
 // the automatic dispatch for block size 512 and <= 1024 taps (ltv_fir.cu).  Logic additionally pinned on the CPU by
@@ -124,11 +125,16 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
     // spectrum of frame g per job: bins k = tid + 128 u; thread 0 additionally holds DC (u = 0) and Nyquist (real)
     float2 Hp[NJ][kBins];
     float HpN[NJ];
-    const int gs = max(h0 - 1, 0), ge = min(h1, nF - 1);
+    // Input hops are always transformed in the SAME pairs (2m, 2m+1), whatever the chunking: G is even, so the first hop
+    // that reaches this chunk (h0 - 1, odd) is processed together with h0 - 2 and the last one (h1, even) with h1 + 1,
+    // whose own contributions fall outside the chunk and are masked.  The partner of a pair only enters through the
+    // round-off of the shared transforms, so this costs two extra hops per chunk and makes every output sample
+    // bit-identical for any G, batch split or shard.
+    const int gs = max(h0 - 2, 0), ge = min(h1, nF - 1);
 
     // ---- prologue: spectra of frame gs ----
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs, gs, false);
+    for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs - 1, gs, true);    // exactly the (h_{g+1}, h_{g+2}) pair of hops gs-2, gs-1
     __syncthreads();
     fft_forward<N, NJ, PK>(F + 2 * NJ * kPad, tw2, tw3, tid);
 #pragma unroll
@@ -138,10 +144,10 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
         for (int u = 0; u < kBins; ++u) {
             const int k = tid + u * kThreads;
             float2 unused;
-            if (k == 0) Hp[j][u] = make_float2(H[padi(0)].x, 0.f);
-            else split2(H[padi(k)], H[padi(kN - k)], Hp[j][u], unused);
+            if (k == 0) Hp[j][u] = make_float2(H[padi(0)].y, 0.f);
+            else split2(H[padi(k)], H[padi(kN - k)], unused, Hp[j][u]);
         }
-        HpN[j] = H[padi(kN / 2)].x;                                 // only thread 0 uses it
+        HpN[j] = H[padi(kN / 2)].y;                                 // only thread 0 uses it
     }
     __syncthreads();
 
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
 
 #pragma unroll 1
     for (int g = gs; g <= ge; g += 2) {
-        const bool has_b = g + 1 <= ge;
+        const bool has_b = g + 1 <= nF - 1;           // the pair's second hop exists (a property of the utterance only)
         // ---- forward: both hops of every job and the impulse-response pairs as one batch ----
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -228,19 +234,21 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
             const float2* Y = F + j * kPad;
             float* rj = ring + j * kRing;
             const int base = g * kHop - (p.job[j].L >> 1) - t_lo;
-#pragma unroll
-            for (int u = 0; u < kN / kThreads; ++u) {
+            const int nvalid = kHop + p.job[j].L - 1;            // length of the linear convolution; the rest of the
+#pragma unroll                                                    // transform holds only round-off and must not spill
+            for (int u = 0; u < kN / kThreads; ++u) {            // into later hops (nor wrap around the ring)
                 const int n = tid + u * kThreads;
                 const float2 v = Y[padi(n)];
                 const int ra = base + n, rb = ra + kHop;
-                if (ra >= 0 && ra < t_hi - t_lo) rj[ra & (kRing - 1)] += v.y * (1.0f / kN);
-                if (has_b && rb >= 0 && rb < t_hi - t_lo) rj[rb & (kRing - 1)] += v.x * (1.0f / kN);
+                const bool live = n < nvalid;
+                if (live && ra >= 0 && ra < t_hi - t_lo) rj[ra & (kRing - 1)] += v.y * (1.0f / kN);
+                if (live && has_b && rb >= 0 && rb < t_hi - t_lo) rj[rb & (kRing - 1)] += v.x * (1.0f / kN);
             }
         }
         __syncthreads();
         // complete now: every hop below the last input hop just added
-        if (g - 1 >= h0) emit(g - 1);
-        if (has_b && g >= h0) emit(g);
+        if (g - 1 >= h0 && g - 1 < h1) emit(g - 1);
+        if (has_b && g >= h0 && g < h1) emit(g);
         // no barrier needed here: emit touches only the rings, the next iteration's loads only F (whose last reads
         // were ordered by the barrier above), and the rings are next written after the FFT passes' barriers
     }

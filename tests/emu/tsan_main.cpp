@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
     const int B = 1, nF = 7, L = 510, T = nF * 512;
     std::vector<float> x1(B * T), x2(B * T), ir1(B * nF * L), ir2(B * nF * L), y1(B * T), y2(B * T), mix(B * T), add(B * T);
     fill(x1, 1.f); fill(x2, 1.f); fill(ir1, 0.05f); fill(ir2, 0.05f); fill(add, 1.f);
-    emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), x2.data(), ir2.data(), L, y2.data(), add.data(), mix.data(), 1, 0, B, nF, 3);
+    emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), x2.data(), ir2.data(), L, y2.data(), add.data(), mix.data(), 1, 0, B, nF, 4);
     emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), nullptr, ir2.data(), 254, y2.data(), nullptr, mix.data(), 1, 0, B, nF, 32);
     emu_ltv_fir_fft(x1.data(), ir1.data(), L, y1.data(), nullptr, nullptr, 0, nullptr, nullptr, mix.data(), 1, 0, B, nF, 2);
     {   // 2048-point instance (1022 taps)

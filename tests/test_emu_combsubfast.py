@@ -64,7 +64,7 @@ def _comb_fp32(name_or_inputs):
 
 
 @pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "combsubfast"])
-@pytest.mark.parametrize("hops", [32, 16, 8, 5, 4, 2, 1])
+@pytest.mark.parametrize("hops", [32, 16, 8, 4, 2])
 def test_kernel_source_matches_reference_golden(emu, name, hops):
     inp = G.build_inputs(name)
     gold = util.load_golden(name)
@@ -97,3 +97,16 @@ def test_kernel_source_in_kernel_noise_is_shard_invariant(emu):
     assert np.array_equal(full[1:], part) and np.isfinite(full).all()
     silent = emu(np.zeros_like(comb), dense.numpy(), None, seed=4)       # noise branch alone: non-trivial output
     assert 1e-4 < util.rms(silent) < 1.0
+
+
+def test_output_is_bit_identical_for_any_chunking(emu):
+    """frames are always transformed in the same (2m, 2m+1) pairs, so the hops-per-CTA choice (adapted to the batch size
+    by the launcher) cannot change a single bit"""
+    inp = G.build_inputs("csfast_b2_f24")
+    comb, dense, noise = _comb_fp32(inp), inp["dense"].numpy(), inp["noise"].numpy()
+    ref = emu(comb, dense, noise, G_hops=32)
+    for hops in (2, 4, 8, 16):
+        assert np.array_equal(emu(comb, dense, noise, G_hops=hops), ref), hops
+    odd = emu(comb[:, :23 * P], dense[:, :23], noise[:, :23 * P], G_hops=32)       # odd frame count
+    for hops in (2, 8):
+        assert np.array_equal(emu(comb[:, :23 * P], dense[:, :23], noise[:, :23 * P], G_hops=hops), odd), hops
