@@ -269,15 +269,12 @@ bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs) {
 template <int N, int NJ, bool PK>
 static int launch_fir_fft_as(const FftFirParams& p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = fir_fft_smem<N, NJ>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
-        }
-        cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
+    // per launch, like the direct-form kernels: function attributes are per device and this costs ~1 us
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
     }
+    cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     ltv_fir_fft_kernel<N, NJ, PK><<<grid, kThreads, smem, st>>>(p);
     return check_launch("ltv_fir(fft)");
 }

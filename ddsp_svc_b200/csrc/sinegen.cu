@@ -373,12 +373,9 @@ __global__ void __launch_bounds__(kThreads4, 6) sinegen4_kernel(SgParams p) {
 
 template <int DIM, bool FUSED, int MODE>
 void launch_v2_as(const SgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    static bool carveout_set = false;            // 18 KB tiles x 6 resident CTAs: ask for the large shared-memory split
-    if (!carveout_set) {
-        cudaFuncSetAttribute(sinegen4_kernel<DIM, FUSED, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-    }
+    // 18 KB tiles x 6 resident CTAs: ask for the large shared-memory split (per launch: attributes are per device)
+    cudaFuncSetAttribute(sinegen4_kernel<DIM, FUSED, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     sinegen4_kernel<DIM, FUSED, MODE><<<grid, kThreads4, smem, st>>>(p);
 }
 
