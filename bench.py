@@ -319,12 +319,14 @@ class Runner:
             self.fixed.ctrls = full
 
     # the same through HOST buffers: pinned inputs -> H2D -> public module API -> D2H of the result
+    e2e_streams = 1
+
     def step_e2e(self, chunks=4):
         """public API with host buffers: HostPipeline (chunked upload | kernels | download) around the module's
         forward; returns the event to synchronise on."""
         from ddsp_svc_b200 import HostPipeline
         if getattr(self, "_pipe", None) is None or self._pipe.chunks != chunks:
-            self._pipe = HostPipeline(self.dev, chunks=chunks)
+            self._pipe = HostPipeline(self.dev, chunks=chunks, compute_streams=self.e2e_streams)
         host = {"f0": self.f0_h}
         if not self.sg:
             host["dense"] = self.dense_h
@@ -413,6 +415,8 @@ def main():
                     help="utterance chunks of the host-buffer pipeline: a count (1 = serial) or comma-separated "
                          "relative sizes (default tapered: short fill and drain; measured 2.57 ms vs 2.72 ms "
                          "for 4 equal chunks on the Sins workload)")
+    ap.add_argument("--e2e-streams", type=int, default=1,
+                    help="compute streams of the host-buffer pipeline (HostPipeline(compute_streams=...); >1 not yet measured)")
     ap.add_argument("--fir-impl", default="auto", choices=["auto", "cuda", "tc", "cuda8", "fft"],
                     help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
     ap.add_argument("--fft-arith", default="scalar", choices=["scalar", "packed"],
@@ -443,6 +447,7 @@ def main():
 
     run = Runner(w, dev, rank, torch)
     e2e_chunks = int(args.e2e_chunks) if args.e2e_chunks.isdigit() else tuple(int(x) for x in args.e2e_chunks.split(","))
+    run.e2e_streams = args.e2e_streams
     if args.sinegen_impl != "auto":
         run.ops.set_sinegen_impl(args.sinegen_impl)
     if args.fir_impl != "auto":

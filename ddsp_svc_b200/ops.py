@@ -91,6 +91,8 @@ def dft_tables(n_mag, device):
             t = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
             _lib.check(L.b2d_dft_tables(int(n_mag), t.data_ptr(), _stream()), "b2d_dft_tables")
             _count(2)
+            # built once per device and then read from whatever stream the caller is on: make it visible to all of them
+            torch.cuda.current_stream().synchronize()
             _tables[key] = t
     return t
 

@@ -40,11 +40,16 @@ def chunk_bounds(batch, chunks):
 
 
 class HostPipeline:
-    def __init__(self, device, chunks=4):
+    def __init__(self, device, chunks=4, compute_streams=1):
+        """``compute_streams`` > 1 (opt-in, not yet measured): consecutive chunks run on alternating side streams, so the
+        small frame-rate kernels of chunk c+1 (which fill a fraction of the GPU) can overlap the FIR of chunk c instead
+        of queueing behind it.  1 = everything on the caller's current stream (the measured configuration)."""
         self.device = torch.device(device)
         self.chunks = int(chunks) if isinstance(chunks, int) else tuple(chunks)
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
+        self.compute = [torch.cuda.Stream(device=self.device) for _ in range(int(compute_streams))] \
+            if int(compute_streams) > 1 else []
         self._dev = {}
 
     def _device_like(self, name, host):
@@ -78,11 +83,15 @@ class HostPipeline:
                 ev = torch.cuda.Event()
                 ev.record(self.h2d)
             up.append(ev)
-        for (lo, hi), ev in zip(bounds, up):
-            main.wait_event(ev)
-            out = forward_chunk({k: t[lo:hi] for k, t in dev.items()}, lo, hi)
-            done = torch.cuda.Event()
-            done.record(main)
+        for s in self.compute:
+            s.wait_stream(main)
+        for c, ((lo, hi), ev) in enumerate(zip(bounds, up)):
+            cs = self.compute[c % len(self.compute)] if self.compute else main
+            with torch.cuda.stream(cs):                 # a no-op context when cs is the current stream
+                cs.wait_event(ev)
+                out = forward_chunk({k: t[lo:hi] for k, t in dev.items()}, lo, hi)
+                done = torch.cuda.Event()
+                done.record(cs)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(done)
                 out_host[lo:hi].copy_(out, non_blocking=True)
@@ -90,4 +99,6 @@ class HostPipeline:
         fin = torch.cuda.Event()
         fin.record(self.d2h)
         main.wait_stream(self.d2h)
+        for s in self.compute:
+            main.wait_stream(s)
         return fin
