@@ -155,3 +155,28 @@ def test_output_is_bit_identical_for_any_chunking(emu, L):
         out = emu(x1, ir1, x2, ir2, hops=hops)
         for k in ("y1", "y2", "mix"):
             assert np.array_equal(out[k], ref[k]), (hops, k)
+
+
+def test_random_shapes_fuzz(emu):
+    """25 random (batch, frames, hops per CTA, tap counts, one / two jobs, addend) combinations against the closed form"""
+    rng = np.random.default_rng(123)
+    for it in range(25):
+        B, nF, hops = int(rng.integers(1, 3)), int(rng.integers(1, 12)), int(rng.choice([2, 4, 8, 16, 32]))
+        L1 = int(rng.choice([2, 4, 64, 254, 510, 512, 514, 800, 1022, 1024]))
+        two = bool(rng.integers(0, 2))
+        L2 = int(rng.choice([2, 254, 510, 512, 1022]))
+        x1 = rng.standard_normal((B, nF * P)).astype(np.float32)
+        ir1 = (rng.standard_normal((B, nF, L1)) / np.sqrt(L1)).astype(np.float32)
+        x2 = rng.standard_normal((B, nF * P)).astype(np.float32) if two else None
+        ir2 = (rng.standard_normal((B, nF, L2)) / np.sqrt(L2)).astype(np.float32) if two else None
+        add = rng.standard_normal((B, nF * P)).astype(np.float32) if rng.integers(0, 2) else None
+        out = emu(x1, ir1, x2, ir2, addend=add, hops=hops, want=("y1", "y2", "mix") if two else ("y1", "mix"))
+        tag = (it, B, nF, hops, L1, L2 if two else 0)
+        assert np.abs(out["y1"] - cf.ltv_fir(x1.astype(np.float64), ir1.astype(np.float64), P)).max() < 1e-5, tag
+        want = out["y1"]
+        if two:
+            assert np.abs(out["y2"] - cf.ltv_fir(x2.astype(np.float64), ir2.astype(np.float64), P)).max() < 1e-5, tag
+            want = want + out["y2"]
+        if add is not None:
+            want = want + add
+        assert np.array_equal(out["mix"], want), tag
