@@ -1,5 +1,5 @@
 """ddsp_svc_b200 -- B200 (sm_100a) kernels for the DDSP harmonic-plus-noise synthesis path of
-yxlllc/DDSP-SVC, behind the reference's Sins / CombSub / CombSubSuperFast / SineGen forward()
+yxlllc/DDSP-SVC, behind the reference's Sins / CombSub / CombSubFast / CombSubSuperFast / SineGen forward()
 API.  See DESIGN.md for the path, its boundary and the kernels; include/b200ddsp.h for the C ABI.
 """
 from . import _lib, ops, sharding, synthetic  # noqa: F401
