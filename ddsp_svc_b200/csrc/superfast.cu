@@ -29,7 +29,9 @@
 // The reference's fp32 operation order is kept for the source (its in-frame phase is fp32 and the
 // sinc argument amplifies rounding by 1/s), the frame scan accumulates in fp64 like torch's CPU
 // cumsum.  Noise: explicit N(0,1) samples (parity) or in-kernel Philox + Box-Muller.
+#ifndef B2D_HOST_EMU               // tests/emu/ runs the main kernel's source on the CPU (host_emu.h provides the shims)
 #include "b2d_common.cuh"
+#endif
 #include "fft_regs.cuh"
 
 namespace {
@@ -42,6 +44,7 @@ constexpr int kScanThreads = 256;
 
 __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
 
+#ifndef B2D_HOST_EMU               // warp shuffles: not emulated (the test computes its output with numpy)
 // ---- frame scan: per-frame (s, ds, acc_prev) and phase_frames  (vocoder.py:641-650) ----------
 __global__ void __launch_bounds__(kScanThreads)
 superfast_scan_kernel(const float* __restrict__ f0, int nF, int P, float sr, float4* __restrict__ frame_par,
@@ -85,6 +88,8 @@ superfast_scan_kernel(const float* __restrict__ f0, int nF, int P, float sr, flo
         run += (double)adv(k);
     }
 }
+
+#endif
 
 using namespace b2d_fft;   // cadd / csub / cmul / Dft<R>: register DFTs shared with combsubfast.cu
 
@@ -407,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 3) superfast_kernel(SfParams p) {
 
 }  // namespace
 
+#ifndef B2D_HOST_EMU
 extern "C" size_t b2d_superfast_workspace_bytes(int B, int n_frames) {
     if (B <= 0 || n_frames <= 0) return 0;
     return (size_t)B * n_frames * sizeof(float4);
@@ -459,3 +465,4 @@ extern "C" int b2d_superfast_synth(const void* workspace, const float* c_harmoni
     if (rc) return rc;
     return b2d::check_launch("superfast_synth");
 }
+#endif  // B2D_HOST_EMU

@@ -69,6 +69,19 @@ inline float sinpif(float x) { return (float)std::sin(M_PI * (double)x); }
 inline void sincospif(float x, float* s, float* c) { *s = sinpif(x); *c = cospif(x); }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 
+// IEEE single operations (build with -ffp-contract=off so the host compiler does not fuse them) and the fast-math
+// intrinsics (libm accuracy instead of the SFU's: the emulated tests compare with tolerances that cover both)
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __sinf(float x) { return std::sin(x); }
+inline float __cosf(float x) { return std::cos(x); }
+inline float __expf(float x) { return std::exp(x); }
+inline float __logf(float x) { return std::log(x); }
+inline void __sincosf(float x, float* s, float* c) { *s = std::sin(x); *c = std::cos(x); }
+
 #define B2D_PI_F 3.14159265358979323846f
 #define B2D_TWO_PI_F 6.28318530717958647692f
 

@@ -11,6 +11,8 @@
 #include "emu_ltv_fir_fft.cpp"
 #elif defined(TSAN_CSFAST)
 #include "emu_combsubfast.cpp"
+#elif defined(TSAN_SUPERFAST)
+#include "emu_superfast.cpp"
 #else
 #define B2D_HOST_EMU 1
 #include "host_emu.h"
@@ -49,6 +51,14 @@ int main(int argc, char** argv) {
     fill(comb, 1.f); fill(noise, 1.f); fill(dense, 0.3f, -1.f);
     emu_combsubfast(comb.data(), dense.data(), dense.data() + 513, dense.data() + 1026, C, noise.data(), 1, 0, B, nF, 4, out.data());
     emu_combsubfast(comb.data(), dense.data(), dense.data() + 513, dense.data() + 1026, C, nullptr, 1, 0, B, nF, 32, out.data());
+    for (float v : out) s += v;
+#elif defined(TSAN_SUPERFAST)
+    const int B = 1, nF = 9, T = nF * 512, C = 4 * 1025;
+    std::vector<float> par(B * nF * 4), noise(B * T), dense(B * nF * C), out(B * T);
+    for (int k = 0; k < nF; ++k) { par[4 * k] = 0.005f + 0.0001f * k; par[4 * k + 1] = k + 1 < nF ? 0.0001f : 0.f; par[4 * k + 2] = 0.1f * k - (int)(0.1f * k); par[4 * k + 3] = 0.f; }
+    fill(noise, 1.f); fill(dense, 0.3f, -1.f);
+    emu_superfast(par.data(), dense.data(), dense.data() + 1025, dense.data() + 2050, dense.data() + 3075, C, noise.data(), 1, 0, B, nF, 5, out.data());
+    emu_superfast(par.data(), dense.data(), dense.data() + 1025, dense.data() + 2050, dense.data() + 3075, C, nullptr, 1, 0, B, nF, 29, out.data());
     for (float v : out) s += v;
 #else
     const bool with_barrier = argc > 1 && std::string(argv[1]) == "ok";
