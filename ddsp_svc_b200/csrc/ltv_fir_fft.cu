@@ -234,9 +234,11 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
             const float2* Y = F + j * kPad;
             float* rj = ring + j * kRing;
             const int base = g * kHop - (p.job[j].L >> 1) - t_lo;
-            const int nvalid = kHop + p.job[j].L - 1;            // length of the linear convolution; the rest of the
-#pragma unroll                                                    // transform holds only round-off and must not spill
-            for (int u = 0; u < kN / kThreads; ++u) {            // into later hops (nor wrap around the ring)
+            // length of the linear convolution; the rest of the transform holds only round-off and must not spill into
+            // later hops (nor wrap around the ring)
+            const int nvalid = kHop + p.job[j].L - 1;
+#pragma unroll
+            for (int u = 0; u < kN / kThreads; ++u) {
                 const int n = tid + u * kThreads;
                 const float2 v = Y[padi(n)];
                 const int ra = base + n, rb = ra + kHop;
