@@ -19,9 +19,8 @@
 //     a hop is complete once the segment of the FOLLOWING input hop has been added and is then written exactly once
 //     (y1, y2 and mix = y1 + y2 (+ addend)) with 128-bit stores -- deterministic, no atomics.
 // 4 FFT-1024 per hop and job pair replace 2 x 2 x L x P = 1.04 M FMAs of the direct form (L = 510): ~4x fewer
-// instructions.  A CTA owns G hops (G even) of one utterance and processes the G+2 input hops that reach them plus the
-// two that complete their pairs; white-noise input (x2 == nullptr) is the same Philox stream as in the direct-form
-// kernels.
+// instructions.  A CTA owns G hops (G even) of one utterance and processes the G+2 input hops that reach them (they
+// form whole pairs); white-noise input (x2 == nullptr) is the same Philox stream as in the direct-form kernels.
 //
 // Measured on B200 (Sins, B = 32 x 10 s, two 510-tap filters): 0.372 ms against 1.18 ms for the direct form -> this is
 // the automatic dispatch for block size 512 and <= 1024 taps (ltv_fir.cu).  Logic additionally pinned on the CPU by
@@ -125,12 +124,11 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
     // spectrum of frame g per job: bins k = tid + 128 u; thread 0 additionally holds DC (u = 0) and Nyquist (real)
     float2 Hp[NJ][kBins];
     float HpN[NJ];
-    // Input hops are always transformed in the SAME pairs (2m, 2m+1), whatever the chunking: G is even, so the first hop
-    // that reaches this chunk (h0 - 1, odd) is processed together with h0 - 2 and the last one (h1, even) with h1 + 1,
-    // whose own contributions fall outside the chunk and are masked.  The partner of a pair only enters through the
-    // round-off of the shared transforms, so this costs two extra hops per chunk and makes every output sample
-    // bit-identical for any G, batch split or shard.
-    const int gs = max(h0 - 2, 0), ge = min(h1, nF - 1);
+    // Input hops are always transformed in the SAME pairs (2m-1, 2m), whatever the chunking: G is even, so the first hop
+    // that reaches this chunk (h0 - 1, odd) starts a pair and the last one (h1, even) ends one -- no extra work, and
+    // since the partner of a pair only enters through the round-off of the shared transforms, every output sample is
+    // bit-identical for any G, batch split or shard.  Hop -1 (the partner of hop 0) does not exist: zeros.
+    const int gs = h0 - 1, ge = min(h1, nF - 1);
 
     // ---- prologue: spectra of frame gs ----
 #pragma unroll
@@ -176,11 +174,11 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
 
 #pragma unroll 1
     for (int g = gs; g <= ge; g += 2) {
-        const bool has_b = g + 1 <= nF - 1;           // the pair's second hop exists (a property of the utterance only)
+        const bool has_a = g >= 0, has_b = g + 1 <= nF - 1;      // properties of the utterance only, not of the chunking
         // ---- forward: both hops of every job and the impulse-response pairs as one batch ----
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            load_x(j, g, true, F + j * kPad);
+            load_x(j, g, has_a, F + j * kPad);
             load_x(j, g + 1, has_b, F + (NJ + j) * kPad);
             load_ir_pair(j, g + 1, g + 2, true);
         }
@@ -243,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
                 const float2 v = Y[padi(n)];
                 const int ra = base + n, rb = ra + kHop;
                 const bool live = n < nvalid;
-                if (live && ra >= 0 && ra < t_hi - t_lo) rj[ra & (kRing - 1)] += v.y * (1.0f / kN);
+                if (live && has_a && ra >= 0 && ra < t_hi - t_lo) rj[ra & (kRing - 1)] += v.y * (1.0f / kN);
                 if (live && has_b && rb >= 0 && rb < t_hi - t_lo) rj[rb & (kRing - 1)] += v.x * (1.0f / kN);
             }
         }
