@@ -24,6 +24,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SR, P = 44100, 512
+OTHER_WORKLOADS = ("sins_cfg1", "combsub", "superfast", "combsubfast", "sinegen", "srcmod")
+
+# N -> (gather mode, chunks, compute streams) chosen by `--gather auto` (measured on B200)
+AUTO_GATHER = {2: ("peer", 1, 1), 4: ("peer", 1, 1), 8: ("peer-copy", 4, 2)}
+
 WORKLOADS = {
     # name: (kind, batch per GPU, seconds, params, algorithmic bytes per output sample)
     "sins": dict(kind="sins", B=32, sec=10, H=128, Ma=256, Mn=256,
@@ -306,15 +311,16 @@ class Runner:
     def row_len(self):
         return self.T * self.width
 
-    def step_rows(self, lo, hi):
+    def step_rows(self, lo, hi, signal_out=None):
         f0 = self.f0_d[lo:hi]
         if self.sg:
             out = self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B + lo)
             return out.reshape(hi - lo, -1)
         full = self.fixed.ctrls
         self.fixed.ctrls = self.syn.split_views(self.dense_d[lo:hi], self.sm)
+        kw = {"signal_out": signal_out} if signal_out is not None else {}
         try:
-            return self.model(None, f0, None, utterance_offset=self.rank * self.B + lo)[0]
+            return self.model(None, f0, None, utterance_offset=self.rank * self.B + lo, **kw)[0]
         finally:
             self.fixed.ctrls = full
 
@@ -396,6 +402,86 @@ class Runner:
                 "ltv_fir_harmonic_1022": lambda: ops.ltv_fir(comb, ir_h, P)}
 
 
+def time_e2e(run, chunks, flush, reps, torch):
+    ee = []
+    for i in range(reps + 1):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run.step_e2e(chunks).synchronize()
+        b.record()                     # recorded on the main stream, which waits for the download stream
+        b.synchronize()
+        if i > 0:
+            ee.append(a.elapsed_time(b))
+    return sum(ee) / len(ee)
+
+
+def time_kernels(run, flush, reps, torch):
+    kt = {}
+    for name, fn in run.kernels().items():
+        ts = []
+        fn()                               # untimed: first use of this call path
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        kt[name] = statistics.median(ts)   # average launch duration, robust to a stray slow launch
+    return kt
+
+
+def time_other_workload(name, dev, flush, torch, steps=10, warmup=3):
+    """One more workload of the path, device-timed like the headline (L2 flushed, CUDA events per step): the numbers the
+    single BENCH line carries under `other_workloads` so every default kernel has a driver-visible timing."""
+    w = WORKLOADS[name]
+    run = Runner(w, dev, 0, torch)
+    for _ in range(warmup):
+        run.step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(); run.step(); b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    e2e_ms = time_e2e(run, (4, 8, 12, 6, 2) if w["B"] >= 16 else 1, flush, 3, torch)
+    kt = time_kernels(run, flush, 5, torch)
+    peak, _ = measured_peak_hbm()
+    dom = max(kt, key=kt.get)
+    alg = algorithmic_bytes(w, run.nF)
+    n = w["B"] * run.T
+    out = {"workload": w["label"], "value": n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+           "e2e_value": n / (e2e_ms * 1e-3) / 1e6, "e2e_ms_per_step": e2e_ms,
+           "roofline": {"kernel": dom, "frac": alg / (kt[dom] * 1e-3) / 1e9 / peak,
+                        "whole_path_frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
+                        "traffic": ncu_traffic(name, dom), "kernel_ms": kt}}
+    del run
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_gpu_baseline(w, run, flush, torch, reps=3):
+    """The secondary bar of SURVEY 8(d): the reference's own algorithm under eager PyTorch on THIS GPU (oracle port =
+    the same ATen operators as ddsp/vocoder.py:556-611, here on device='cuda'), full batch, CUDA-event timed.  A
+    baseline only -- nothing of it is on the product path."""
+    if run.sg or run.sm is None:
+        f0, ctrls = run.f0_d, None
+    else:
+        f0, ctrls = run.f0_d, run.ctrl_d
+    oracle_forward(w, f0[:2], {k: v[:2] for k, v in ctrls.items()} if ctrls else None)     # cuFFT plans, allocator
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); oracle_forward(w, f0, ctrls); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    torch.cuda.empty_cache()
+    ms = min(ts)
+    return {"value": w["B"] * run.T / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "kind": "port",
+            "what": "oracle port of the reference (same ATen operators) run eagerly on this GPU, full batch, "
+                    "inputs resident in HBM, best of %d" % reps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -405,12 +491,18 @@ def main():
     ap.add_argument("--workload", default="sins", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the waveform")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-copy", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-chunks", "peer-copy", "nccl"],
                     help="N>1: 'peer' = the FIR kernel stores the waveform into rank 0's peer-mapped buffer; "
-                         "'peer-copy' = chunked synthesis + copy-engine DMA into that buffer; 'nccl' = gather; "
-                         "'auto' = peer for N<=4, peer-copy with 2 chunks for N=8 (measured)")
+                         "'peer-chunks' = the same per chunk of utterances; 'peer-copy' = chunked synthesis + copy-engine "
+                         "DMA into that buffer; 'nccl' = gather; 'auto' = the measured best per N (AUTO_GATHER)")
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N>1: split the local batch into this many chunks and overlap their gather with synthesis")
+    ap.add_argument("--gather-streams", type=int, default=1,
+                    help="N>1, chunked peer modes: compute streams the chunks alternate between")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the eager-PyTorch-on-GPU baseline and the `other_workloads` timings of the default run")
+    ap.add_argument("--quick", action="store_true",
+                    help="device-timed step only: skip the host-buffer e2e, per-kernel and CPU legs (sweeps)")
     ap.add_argument("--e2e-chunks", default="4,8,12,6,2",
                     help="utterance chunks of the host-buffer pipeline: a count (1 = serial) or comma-separated "
                          "relative sizes (default tapered: short fill and drain; measured 2.57 ms vs 2.72 ms "
@@ -421,6 +513,9 @@ def main():
                     help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
     ap.add_argument("--fft-arith", default="scalar", choices=["scalar", "packed"],
                     help="A/B switch: packed f32x2 complex additions in the FFT kernels (ops.set_fft_arith)")
+    ap.add_argument("--overlap", type=int, default=None,
+                    help="A/B switch (ops.set_overlap): 0 in order, 1 impulse responses beside the bank, k >= 2 "
+                         "additionally k staggered sub-batches on two streams")
     ap.add_argument("--sinegen-impl", default="auto", choices=["auto", "v1", "v2", "v2p"],
                     help="A/B switch for the SineGen / source-module kernel (ops.set_sinegen_impl)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
@@ -452,49 +547,70 @@ def main():
         run.ops.set_sinegen_impl(args.sinegen_impl)
     if args.fir_impl != "auto":
         run.ops.set_fir_impl(args.fir_impl)
+    if args.overlap is not None:
+        run.ops.set_overlap(args.overlap)
     if args.fft_arith != "scalar":
         run.ops.set_fft_arith(args.fft_arith)
     B, nF, T = run.B, run.nF, run.T
     do_gather = world > 1 and not args.no_gather
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    n_chunks = args.gather_chunks
+    n_chunks, n_streams = args.gather_chunks, args.gather_streams
     peer = None
     mode = args.gather
     if mode == "auto":
-        # measured on B200, ms/step (peer stores | 2-chunk DMA push | NCCL gather): N=2 1.73 | - | 1.86,
-        # N=4 1.77 | 1.91 | 2.01, N=8 2.57 | 2.04 | 2.28
-        mode = "peer" if world <= 4 else "peer-copy"
-        if mode == "peer-copy":
-            n_chunks = 2
-    if do_gather and mode in ("peer", "peer-copy") and w["kind"] == "sins":
+        mode, n_chunks, n_streams = AUTO_GATHER.get(world, AUTO_GATHER[8])
+    if do_gather and mode.startswith("peer") and w["kind"] == "sins":
         try:                                   # rank 0's buffer peer-mapped on every rank (NVLink)
             peer = sharding.PeerGather(B, T, dev, dst=0)
         except Exception as e:                 # symmetric memory unavailable: use the NCCL gather
             if rank == 0:
                 print("peer gather unavailable (%s); using NCCL" % (str(e).splitlines()[0][:120],), file=sys.stderr)
             peer = None
-    if peer is None and mode in ("peer", "peer-copy"):
+    if peer is None and mode.startswith("peer"):
         mode = "nccl"
     gather_mode = {"peer": "peer-mapped stores over NVLink from the FIR kernel + device barrier",
-                   "peer-copy": "%d chunks, copy-engine DMA of finished chunks into rank 0's peer-mapped buffer" % max(n_chunks, 2),
+                   "peer-chunks": "%d chunks on %d compute stream(s), each chunk's FIR kernel stores into rank 0's "
+                                  "peer-mapped buffer" % (n_chunks, n_streams),
+                   "peer-copy": "%d chunks on %d compute stream(s), copy-engine DMA of finished chunks into rank 0's "
+                                "peer-mapped buffer" % (n_chunks, n_streams),
                    "nccl": "NCCL gather, %d chunk(s)" % n_chunks}[mode] if do_gather else "none"
 
     def step():
         if not do_gather:
             return run.step()
-        if peer is not None and mode == "peer":
-            sig = run.model(None, run.f0_d, None, utterance_offset=rank * B, signal_out=peer.my_rows)[0]
-            peer.finish()
-            return sig
-        if peer is not None:
-            return sharding.synthesize_and_push(run.step_rows, peer, B, dev, chunks=max(n_chunks, 2))
+        if mode == "peer":
+            run.model(None, run.f0_d, None, utterance_offset=rank * B, signal_out=peer.my_rows)
+            return peer.finish()
+        if mode in ("peer-copy", "peer-chunks"):
+            return sharding.synthesize_and_push(run.step_rows, peer, B, dev, chunks=n_chunks, streams=n_streams,
+                                                direct=mode == "peer-chunks")
         if n_chunks <= 1:
             sig = run.step()
-            sharding.gather_waveform(sig.reshape(B, -1), world * B, dst=0)
-            return sig
+            return sharding.gather_waveform(sig.reshape(B, -1), world * B, dst=0)
         # chunked: the NCCL transfer of finished utterances overlaps the synthesis of the rest
         return sharding.synthesize_and_gather(run.step_rows, B, world * B, run.row_len, dev, dst=0, chunks=n_chunks)
+
+    def check_gather():
+        """Untimed: one more step with the same host seed on every rank, then rank 0 re-synthesizes every rank's
+        utterances locally (that rank's seeded inputs, utterance_offset = r*B, same chunking -> same seed draws) and
+        compares them bit for bit with the rows that arrived."""
+        torch.manual_seed(4242)
+        got = step()
+        sync_all()
+        if rank != 0:
+            return None
+        bad = 0
+        for r in range(world):
+            other = Runner(w, dev, r, torch) if r else run
+            torch.manual_seed(4242)
+            if mode in ("peer-copy", "peer-chunks") or (mode == "nccl" and n_chunks > 1):
+                want = torch.cat([other.step_rows(lo, hi) for lo, hi in sharding._chunk_bounds(B, n_chunks)])
+            else:
+                want = other.step()
+            bad += int(not torch.equal(got[r * B:(r + 1) * B], want.reshape(B, -1)))
+            del other, want
+        return bad == 0
 
     def sync_all():
         torch.cuda.synchronize()
@@ -522,33 +638,16 @@ def main():
         wall = time.perf_counter() - wall0
         launches = ops.launches() - n0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        gather_checked = check_gather() if do_gather else None
 
         # ---- end to end through the public module API with HOST buffers ----
-        ee = []
-        for i in range(max(3, min(args.steps, 10)) + 1):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            run.step_e2e(e2e_chunks).synchronize()
-            b.record()                     # recorded on the main stream, which waits for the download stream
-            b.synchronize()
-            if i > 0:
-                ee.append(a.elapsed_time(b))
-        e2e_ms = sum(ee) / len(ee)
+        e2e_ms = float("nan")
+        if not args.quick:
+            e2e_ms = time_e2e(run, e2e_chunks, flush, max(3, min(args.steps, 10)), torch)
         clk = clocks.stop() if rank == 0 else None
 
         # ---- per-kernel durations (CUDA events on the launching stream), for the roofline ----
-        kt = {}
-        reps = max(5, min(args.steps, 20))
-        for name, fn in run.kernels().items():
-            ts = []
-            fn()                               # untimed: first use of this call path
-            for _ in range(reps):
-                flush.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record(); b.synchronize()
-                ts.append(a.elapsed_time(b))
-            kt[name] = statistics.median(ts)   # average launch duration, robust to a stray slow launch
+        kt = time_kernels(run, flush, max(5, min(args.steps, 20)), torch) if not args.quick else {}
 
     # ---- reduce over ranks: max device time ----
     if world > 1:
@@ -561,8 +660,15 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        dom = max(kt, key=kt.get)
         alg_bytes = algorithmic_bytes(w, nF)
+        if args.quick:
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms_per_step, "value": value,
+                              "gather": gather_mode, "gather_checked": gather_checked,
+                              "sm_mhz": clk and clk.get("sm_mhz")}))
+            if world > 1:
+                dist.destroy_process_group()
+            return
+        dom = max(kt, key=kt.get)
         achieved = alg_bytes / (kt[dom] * 1e-3) / 1e9
         line = {
             "metric": metric_name(w),
@@ -590,6 +696,12 @@ def main():
             "gpu_launches": launches,
             "clocks": clk,
         }
+        if do_gather:
+            line["gather_checked"] = gather_checked
+        if world == 1 and args.workload == "sins" and not args.no_others:
+            with torch.no_grad():
+                line["eager_gpu_baseline"] = eager_gpu_baseline(w, run, flush, torch)
+                line["other_workloads"] = {n: time_other_workload(n, dev, flush, torch) for n in OTHER_WORKLOADS}
         if world == 1 and not args.no_cpu_baseline:
             sample_b = 4 if w["B"] >= 4 else w["B"]
             v, dt, cores = cpu_reference_run(w, sample_b, 3)

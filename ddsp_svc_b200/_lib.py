@@ -12,7 +12,8 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libb200ddsp.so")
+# B2D_LIB_PATH: load another build of the same library (A/B runs of compile-time variants; development only)
+LIB_PATH = os.environ.get("B2D_LIB_PATH") or os.path.join(HERE, "libb200ddsp.so")
 HEADER = os.path.join(ROOT, "include", "b200ddsp.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -56,6 +57,7 @@ SIGNATURES = {
                                          c_stream]),
     "b2d_set_sinegen_impl": (ctypes.c_int, [ctypes.c_int]),
     "b2d_set_fft_arith": (ctypes.c_int, [ctypes.c_int]),
+    "b2d_set_overlap": (ctypes.c_int, [ctypes.c_int]),
     "b2d_combsubfast_filter": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p, ctypes.c_uint64,
                                               ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32p, c_stream]),
     "b2d_comb_source": (ctypes.c_int, [c_f32p, c_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
@@ -83,25 +85,31 @@ def sources():
 
 
 def _stale():
-    if not os.path.isfile(LIB_PATH):
+    path = os.path.join(HERE, "libb200ddsp.so")
+    if not os.path.isfile(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [HEADER]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into ddsp_svc_b200/libb200ddsp.so (in-tree)."""
-    if not force and not _stale():
-        return LIB_PATH
+def build(force=False, verbose=False, out=None, defines=()):
+    """Compile every CUDA source for sm_100a into ddsp_svc_b200/libb200ddsp.so (in-tree).
+    ``out`` / ``defines``: build a compile-time variant (-DNAME=VALUE ...) into another file for A/B runs
+    (loaded with B2D_LIB_PATH=<file>)."""
+    default = os.path.join(HERE, "libb200ddsp.so")
+    target = out or default
+    if out is None and not force and not _stale():
+        return target
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    cmd = ([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", target] + sources())
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return target
 
 
 def lib():

@@ -28,11 +28,76 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 }  // namespace b2d
 
-namespace b2d { bool g_fft_packed = false; }
+namespace b2d { std::atomic<int> g_fft_packed{0}; }
+
+// ---------------------------------------------------------------------------------------
+// Fork/join inside one synthesizer call.  The impulse-response builds depend only on the raw controls, the oscillator
+// bank / comb source only on f0 + amplitudes, and utterances are independent: the drivers run such kernels side by
+// side on an internal side stream and join it on the caller's stream before returning (event record / wait only: no
+// host synchronisation, legal under stream capture).  Streams and events are cached per host thread and device
+// (thread_local: two threads calling into the library never share an event, so one thread's record can never be
+// picked up by the other's wait).
+//   mode 0: everything on the caller's stream, in order
+//   mode 1: impulse responses on a high-priority side stream next to the bank / comb source
+//   mode k >= 2: additionally the batch is cut into k sub-batches that alternate between the caller's stream and the
+//           side stream, staggered (the side stream starts with the impulse responses of the WHOLE batch), so the
+//           FIR of one sub-batch (shared-memory / latency bound) shares the SMs with the bank of the next (FMA / SFU
+//           bound).  Results do not depend on the mode: the noise is keyed by the global utterance index and the
+//           FFT-domain FIR is bit-identical for any batch split.
+//   mode -k: as k, with the high-priority stream as the side stream
+// ---------------------------------------------------------------------------------------
+namespace b2d {
+std::atomic<int> g_overlap{1};
+
+struct SideLane {
+    cudaStream_t hi = nullptr, lo = nullptr;       // high- and normal-priority side streams
+    cudaEvent_t fork = nullptr, ir_done = nullptr, join = nullptr;
+    bool ok = false;
+};
+struct SideLanes {
+    SideLane lane[64];
+    ~SideLanes() {
+        for (SideLane& l : lane) {
+            if (l.fork) cudaEventDestroy(l.fork);
+            if (l.ir_done) cudaEventDestroy(l.ir_done);
+            if (l.join) cudaEventDestroy(l.join);
+            if (l.hi) cudaStreamDestroy(l.hi);        // deferred by the runtime until queued work has drained
+            if (l.lo) cudaStreamDestroy(l.lo);
+        }
+    }
+};
+
+// nullptr = run everything on the caller's stream (mode 0, or the streams could not be created)
+static SideLane* side_lane() {
+    static thread_local SideLanes lanes;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideLane& l = lanes.lane[dev];
+    if (!l.ok) {
+        if (l.hi) return nullptr;                        // creation failed before: do not retry on every call
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = greatest priority
+        bool good = cudaStreamCreateWithPriority(&l.hi, cudaStreamNonBlocking, hi) == cudaSuccess;
+        good = good && cudaStreamCreateWithFlags(&l.lo, cudaStreamNonBlocking) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&l.ir_done, cudaEventDisableTiming) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!good) { cudaGetLastError(); if (!l.hi) l.hi = (cudaStream_t)1; return nullptr; }
+        l.ok = true;
+    }
+    return &l;
+}
+}  // namespace b2d
+
+extern "C" int b2d_set_overlap(int mode) {
+    if (mode < -64 || mode > 64) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_overlap: %d outside [-64, 64]", mode);
+    b2d::g_overlap.store(mode, std::memory_order_relaxed);
+    return 0;
+}
 
 extern "C" int b2d_set_fft_arith(int packed) {
     if (packed != 0 && packed != 1) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fft_arith: %d not in {0, 1}", packed);
-    b2d::g_fft_packed = packed != 0;
+    b2d::g_fft_packed.store(packed, std::memory_order_relaxed);
     return 0;
 }
 
@@ -69,29 +134,74 @@ extern "C" int b2d_sins_synth(const float* f0_frames, const double* frame_phase,
     float* ir_ap = reinterpret_cast<float*>(ws + b2d::align_up(BT * 4, 256));
     float* ir_n = reinterpret_cast<float*>(ws + b2d::align_up(BT * 4, 256) + b2d::align_up(BF * La * 4, 256));
 
-    int rc = b2d_sins_bank(f0_frames, frame_phase, c_amp, ctrl_stride, B, n_frames, block, n_harmonics,
-                           sampling_rate, round_fp32, sinus, stream);
-    if (rc) return rc;
-    rc = b2d_ir_build(c_group_delay, ctrl_stride, B2D_IR_ALLPASS, nullptr, dft_tables_allpass, B, n_frames,
-                      n_mag_allpass, sampling_rate, ir_ap, stream);
-    if (rc) return rc;
-    rc = b2d_ir_build(c_noise, ctrl_stride, B2D_IR_MAG_HANN, nullptr, dft_tables_noise, B, n_frames, n_mag_noise,
-                      sampling_rate, ir_n, stream);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (La == Ln && block % 256 == 0) {
-        return b2d::ltv_fir_launch(sinus, ir_ap, La, harmonic, noise_in, ir_n, Ln, noise_out, nullptr, signal, seed,
-                                   utterance_offset, B, n_frames, block, st);
-    }
     if (block % 256 != 0)
         return b2d::fail(B2D_ERR_UNSUPPORTED, "sins_synth: block size %d must be a multiple of 256", block);
-    // different tap counts: two launches, the second adds the first's output
-    if (!noise_out) return b2d::fail(B2D_ERR_UNSUPPORTED, "sins_synth: noise_out required when n_mag_allpass != n_mag_noise");
-    rc = b2d::ltv_fir_launch(noise_in, ir_n, Ln, noise_out, nullptr, nullptr, 0, nullptr, nullptr, nullptr, seed,
-                             utterance_offset, B, n_frames, block, st);
+    if (La != Ln && !noise_out) return b2d::fail(B2D_ERR_UNSUPPORTED, "sins_synth: noise_out required when n_mag_allpass != n_mag_noise");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = b2d::g_overlap.load(std::memory_order_relaxed);
+    b2d::SideLane* lane = mode != 0 ? b2d::side_lane() : nullptr;
+    int nsplit = (mode < 0 ? -mode : mode);
+    if (nsplit < 2 || !lane) nsplit = 1;
+    if (nsplit > B) nsplit = B;
+    cudaStream_t side = lane ? ((mode == 1 || mode < 0) ? lane->hi : lane->lo) : st;
+
+    // one sub-batch [b0, b0 + nb): bank, then (after the impulse responses) the FIRs, all on stream `q`
+    auto bank = [&](int b0, int nb, cudaStream_t q) -> int {
+        return b2d_sins_bank(f0_frames + (size_t)b0 * n_frames, frame_phase + (size_t)b0 * n_frames,
+                             c_amp + (size_t)b0 * n_frames * ctrl_stride, ctrl_stride, nb, n_frames, block, n_harmonics,
+                             sampling_rate, round_fp32, sinus + (size_t)b0 * n_frames * block, q);
+    };
+    auto firs = [&](int b0, int nb, cudaStream_t q) -> int {
+        const size_t ot = (size_t)b0 * n_frames * block, of = (size_t)b0 * n_frames;
+        const float* nz_in = noise_in ? noise_in + ot : nullptr;
+        float* harm = harmonic ? harmonic + ot : nullptr;
+        float* nz_out = noise_out ? noise_out + ot : nullptr;
+        if (La == Ln)
+            return b2d::ltv_fir_launch(sinus + ot, ir_ap + of * La, La, harm, nz_in, ir_n + of * Ln, Ln, nz_out, nullptr,
+                                       signal + ot, seed, utterance_offset + b0, nb, n_frames, block, q);
+        // different tap counts: two launches, the second adds the first's output
+        int r = b2d::ltv_fir_launch(nz_in, ir_n + of * Ln, Ln, nz_out, nullptr, nullptr, 0, nullptr, nullptr, nullptr, seed,
+                                    utterance_offset + b0, nb, n_frames, block, q);
+        if (r) return r;
+        return b2d::ltv_fir_launch(sinus + ot, ir_ap + of * La, La, harm, nullptr, nullptr, 0, nullptr, nz_out, signal + ot,
+                                   seed, utterance_offset + b0, nb, n_frames, block, q);
+    };
+    auto irs = [&](cudaStream_t q) -> int {
+        int r = b2d_ir_build(c_group_delay, ctrl_stride, B2D_IR_ALLPASS, nullptr, dft_tables_allpass, B, n_frames,
+                             n_mag_allpass, sampling_rate, ir_ap, q);
+        if (r) return r;
+        return b2d_ir_build(c_noise, ctrl_stride, B2D_IR_MAG_HANN, nullptr, dft_tables_noise, B, n_frames, n_mag_noise,
+                            sampling_rate, ir_n, q);
+    };
+    if (!lane) {                                       // in order on the caller's stream
+        int rc = irs(st);
+        if (!rc) rc = bank(0, B, st);
+        if (!rc) rc = firs(0, B, st);
+        return rc;
+    }
+    // fork: the side stream starts with the impulse responses of the whole batch (launched first: one 512-thread CTA per
+    // SM, latency bound), the caller's stream with the first bank
+    cudaError_t e = cudaEventRecord(lane->fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(side, lane->fork, 0);
+    if (e != cudaSuccess) return b2d::fail((int)e, "sins_synth: fork: %s", cudaGetErrorString(e));
+    int rc = irs(side);
+    e = cudaEventRecord(lane->ir_done, side);
+    bool main_waited = false;
+    for (int s = 0; s < nsplit && !rc && e == cudaSuccess; ++s) {
+        const int b0 = (int)((long long)B * s / nsplit), b1 = (int)((long long)B * (s + 1) / nsplit);
+        const bool on_side = (s & 1) != 0;
+        cudaStream_t q = on_side ? side : st;
+        rc = bank(b0, b1 - b0, q);
+        if (!on_side && !main_waited) { e = cudaStreamWaitEvent(st, lane->ir_done, 0); main_waited = true; }
+        if (!rc && e == cudaSuccess) rc = firs(b0, b1 - b0, q);
+    }
+    // always join, also after a failed launch: the caller's stream must not lose track of the side stream
+    cudaError_t je = cudaEventRecord(lane->join, side);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(st, lane->join, 0);
     if (rc) return rc;
-    return b2d::ltv_fir_launch(sinus, ir_ap, La, harmonic, nullptr, nullptr, 0, nullptr, noise_out, signal, seed,
-                               utterance_offset, B, n_frames, block, st);
+    if (e != cudaSuccess) return b2d::fail((int)e, "sins_synth: event: %s", cudaGetErrorString(e));
+    if (je != cudaSuccess) return b2d::fail((int)je, "sins_synth: join: %s", cudaGetErrorString(je));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------

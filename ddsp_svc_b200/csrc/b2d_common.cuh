@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/b200ddsp.h"
 
@@ -22,7 +23,7 @@ inline int check_launch(const char* what) {
 }
 
 // b2d_set_fft_arith(1): the FFT kernels (ltv_fir_fft, superfast, combsubfast) use packed f32x2 complex additions
-extern bool g_fft_packed;
+extern std::atomic<int> g_fft_packed;   // debug A/B switch (b2d_set_fft_arith), read once per call
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace b2d

@@ -233,7 +233,7 @@ extern "C" int b2d_combsubfast_filter(const float* comb, const float* c_harmonic
     p.G = G;
     p.seed = seed; p.utt_off = utterance_offset;
     const dim3 grid((unsigned)((n_frames + p.G - 1) / p.G), B);
-    if (b2d::g_fft_packed) combsubfast_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
+    if (b2d::g_fft_packed.load(std::memory_order_relaxed)) combsubfast_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
     else combsubfast_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(p);
     return b2d::check_launch("combsubfast");
 }

@@ -230,7 +230,7 @@ int ir_build_tc_launch(const float* c, int64_t ctrl_stride, int mode, const floa
                        int nF, int M, double sr, float* ir, cudaStream_t st);
 size_t tc_image_floats_host(int M);
 // 0 = auto (tensor cores when supported), 1 = CUDA cores, 2 = tensor cores
-static int g_ir_impl = 0;
+static std::atomic<int> g_ir_impl{0};   // debug A/B switch, read once per call
 static inline size_t cc_table_bytes(int n_mag) {
     const size_t b = (size_t)2 * (n_even(n_mag) + n_odd(n_mag)) * n_cols(n_mag) * sizeof(float);
     return (b + 255) / 256 * 256;
@@ -245,7 +245,7 @@ extern "C" size_t b2d_dft_tables_bytes(int n_mag) {
 
 extern "C" int b2d_set_ir_impl(int impl) {
     if (impl < 0 || impl > 2) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_ir_impl: %d", impl);
-    b2d::g_ir_impl = impl;
+    b2d::g_ir_impl.store(impl, std::memory_order_relaxed);
     return 0;
 }
 
@@ -278,7 +278,7 @@ extern "C" int b2d_ir_build(const float* c, int64_t ctrl_stride, int mode, const
     if (mode != B2D_IR_ALLPASS && mode != B2D_IR_MAG_HANN && mode != B2D_IR_MAG_DYNAMIC)
         return b2d::fail(B2D_ERR_UNSUPPORTED, "ir_build: unknown mode %d", mode);
     {
-        const int impl = b2d::g_ir_impl;
+        const int impl = b2d::g_ir_impl.load(std::memory_order_relaxed);
         const bool ok = b2d::ir_tc_supported(mode, n_mag);
         if (impl == 2 && !ok) return b2d::fail(B2D_ERR_UNSUPPORTED, "ir_build: tensor-core path does not support n_mag=%d in mode %d", n_mag, mode);
         if ((impl == 0 || impl == 2) && ok) {

@@ -84,8 +84,18 @@ struct IrTcParams {
 // MODE as in b200ddsp.h.  NACC = 4 (all-pass: Ce Se Co So) or 2 (magnitude: Ce Co).
 // 512 threads: every phase except the 16-term per-frame prefix sum is spread over all 16 warps
 // (the first version ran one thread per frame on 4 warps and was latency bound at 15 % issue).
+// Register cap: one CTA per SM either way (shared memory, TMEM), but with 64 registers x 512 threads the CTA leaves half
+// of the register file to the oscillator-bank CTAs that b2d_sins_synth runs beside it (api.cu, fork/join).
+#ifndef B2D_IR_TC_MAXREG
+#define B2D_IR_TC_MAXREG 0
+#endif
+#if B2D_IR_TC_MAXREG > 0
+#define B2D_IR_TC_BOUNDS __maxnreg__(B2D_IR_TC_MAXREG)
+#else
+#define B2D_IR_TC_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) ir_build_tc_kernel(IrTcParams p) {
+__global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
     constexpr bool kAllpass = (MODE == B2D_IR_ALLPASS);
     constexpr int NACC = kAllpass ? 4 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];

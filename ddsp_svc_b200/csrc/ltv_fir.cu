@@ -496,9 +496,9 @@ int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, 
 // auto = CUDA cores: measured on B200 (B=32 x 10 s, two 510-tap filters) the tcgen05 kernel takes
 // 4.20 ms against 1.26 ms -- with N = 8 columns every MMA re-reads its 4 KB Hankel operand from
 // shared memory for 16 kflop, so it is operand-bandwidth bound (~56 cycles per 128x8x8 MMA).
-static int g_fir_impl = 0;
+static std::atomic<int> g_fir_impl{0};
 // CUDA-core variant: 0 = auto (16 outputs/thread + FFMA2 when the block size is a multiple of 512), 1 = 8 outputs/thread scalar
-static int g_fir_variant = 0;
+static std::atomic<int> g_fir_variant{0};
 
 // what "auto" means: the FFT-domain kernel wherever it applies (block size 512, <= 1024 taps; measured on B200:
 // 0.372 ms against 1.18 ms for Sins' two 510-tap filters, B = 32 x 10 s), the CUDA-core kernel otherwise.
@@ -522,7 +522,8 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
     if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir: batch %d > 65535", B);
     const int njobs = ir2 ? 2 : 1;
     {
-        const int impl = g_fir_impl == 0 ? fir_auto_impl() : g_fir_impl;
+        const int sel = g_fir_impl.load(std::memory_order_relaxed);
+        const int impl = sel == 0 ? fir_auto_impl() : sel;
         const bool tc_ok = (P == 512) && !(njobs == 2 && (taps1 != taps2 || addend));
         if (impl == 4 && ltv_fir_fft_supported(P, taps1, taps2, njobs)) {
             const float* ptrs0[] = {x1, x2, y1, y2, addend, mix};
@@ -572,7 +573,7 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
         kern<<<dim3(ntiles, B), threads, smem, st>>>(p);
         return check_launch("ltv_fir");
     };
-    if (g_fir_variant != 1 && P % 512 == 0) {            // 16 outputs/thread, FFMA2 (one warp per filter at P = 512)
+    if (g_fir_variant.load(std::memory_order_relaxed) != 1 && P % 512 == 0) {            // 16 outputs/thread, FFMA2 (one warp per filter at P = 512)
         const int threads16 = njobs * (P / 16);
         const size_t smem = (size_t)(njobs * (6 * P + 8 + P + (P >> 4) + 8) + P) * sizeof(float);
         auto go16 = [&](auto kern) -> int {
@@ -599,8 +600,8 @@ extern "C" int b2d_set_fir_impl(int impl) {
     // 0 auto, 1 CUDA cores (auto variant), 2 tensor cores, 3 CUDA cores forcing the 8-outputs/thread scalar kernel,
     // 4 FFT domain
     if (impl < 0 || impl > 4) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_fir_impl: %d", impl);
-    b2d::g_fir_impl = (impl == 3) ? 1 : impl;
-    b2d::g_fir_variant = (impl == 3) ? 1 : 0;
+    b2d::g_fir_impl.store((impl == 3) ? 1 : impl, std::memory_order_relaxed);
+    b2d::g_fir_variant.store((impl == 3) ? 1 : 0, std::memory_order_relaxed);
     return 0;
 }
 

@@ -281,7 +281,7 @@ static int launch_fir_fft_as(const FftFirParams& p, dim3 grid, cudaStream_t st) 
 
 template <int N, int NJ>
 static int launch_fir_fft(const FftFirParams& p, dim3 grid, cudaStream_t st) {
-    return g_fft_packed ? launch_fir_fft_as<N, NJ, true>(p, grid, st) : launch_fir_fft_as<N, NJ, false>(p, grid, st);
+    return g_fft_packed.load(std::memory_order_relaxed) ? launch_fir_fft_as<N, NJ, true>(p, grid, st) : launch_fir_fft_as<N, NJ, false>(p, grid, st);
 }
 
 int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,

@@ -393,13 +393,13 @@ void launch_v2(const SgParams& p, int B, long long T, int impl, cudaStream_t st)
     }
 }
 
-int g_sinegen_impl = 0;   // 0 auto, 1 v1 (one sample per thread), 2 v2 scalar, 3 v2 packed f32x2
+std::atomic<int> g_sinegen_impl{0};   // 0 auto, 1 v1 (one sample per thread), 2 v2 scalar, 3 v2 packed f32x2
 
 }  // namespace
 
 extern "C" int b2d_set_sinegen_impl(int impl) {
     if (impl < 0 || impl > 3) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_sinegen_impl: %d not in 0..3", impl);
-    g_sinegen_impl = impl;
+    g_sinegen_impl.store(impl, std::memory_order_relaxed);
     return 0;
 }
 
@@ -456,7 +456,8 @@ static int sinegen_launch(const float* f0, const float* rand_ini, const float* n
     // auto = the scalar 4-samples-per-thread kernel: the packed variant is ~3-5 % faster, but ptxas contracts its
     // mul.rn.f32x2 + add.rn.f32x2 pairs into FFMA2 (one rounding instead of the reference's two), which moves the sine
     // argument by an ulp: max error 3e-6 instead of 3e-8 against the reference (still inside the 2e-6 RMS gate)
-    const int impl = g_sinegen_impl == 0 ? 2 : g_sinegen_impl;
+    const int sel = g_sinegen_impl.load(std::memory_order_relaxed);
+    const int impl = sel == 0 ? 2 : sel;
     if (impl >= 2 && (dim == 9 || dim == 1)) {
         if (dim == 9) launch_v2<9>(p, B, T, impl, st);
         else launch_v2<1>(p, B, T, impl, st);

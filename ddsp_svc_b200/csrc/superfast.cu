@@ -461,7 +461,7 @@ extern "C" int b2d_superfast_synth(const void* workspace, const float* c_harmoni
         kern<<<dim3((n_frames + G - 1) / G, B), kThreads, smem, (cudaStream_t)stream>>>(p);
         return 0;
     };
-    const int rc = b2d::g_fft_packed ? go(superfast_kernel<true>) : go(superfast_kernel<false>);
+    const int rc = b2d::g_fft_packed.load(std::memory_order_relaxed) ? go(superfast_kernel<true>) : go(superfast_kernel<false>);
     if (rc) return rc;
     return b2d::check_launch("superfast_synth");
 }

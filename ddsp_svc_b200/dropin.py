@@ -72,7 +72,9 @@ def load_model(model_path, device="cuda"):
 
 def patch_reference():
     """Swap the synthesizer classes inside the (importable) reference package.  Returns the dict
-    of original classes so a caller can restore them."""
+    of original classes so a caller can restore them; its keys say what was patched.  If the enhancer stack
+    (nsf_hifigan.models) cannot be imported, only the synthesizers are patched and the reason is returned under
+    ``"_not_patched"`` -- any other failure propagates."""
     import ddsp.vocoder as ref_vocoder          # the reference checkout must be on sys.path
     names = ("Sins", "CombSub", "CombSubSuperFast", "CombSubFast")
     saved = {name: getattr(ref_vocoder, name) for name in names}
@@ -80,12 +82,13 @@ def patch_reference():
         setattr(ref_vocoder, name, getattr(vocoder, name))
     try:
         import nsf_hifigan.models as ref_nsf
-        saved["SineGen"] = ref_nsf.SineGen
-        saved["SourceModuleHnNSF"] = ref_nsf.SourceModuleHnNSF
-        ref_nsf.SineGen = sinegen.SineGen
-        ref_nsf.SourceModuleHnNSF = sinegen.SourceModuleHnNSF
-    except Exception:                           # enhancer stack not importable: synthesizers only
-        pass
+    except ImportError as e:                    # enhancer stack not importable: synthesizers only (reported below)
+        saved["_not_patched"] = {"nsf_hifigan.models": "%s: %s" % (type(e).__name__, e)}
+        return saved
+    saved["SineGen"] = ref_nsf.SineGen
+    saved["SourceModuleHnNSF"] = ref_nsf.SourceModuleHnNSF
+    ref_nsf.SineGen = sinegen.SineGen
+    ref_nsf.SourceModuleHnNSF = sinegen.SourceModuleHnNSF
     return saved
 
 

@@ -15,6 +15,7 @@ IR_ALLPASS, IR_MAG_HANN, IR_MAG_DYNAMIC = 0, 1, 2
 # kernel launches issued through this module (bench.py reports it as gpu_launches)
 _launches = 0
 _tables = {}
+_overlap_mode = 1   # mirrors the library's default (b2d_set_overlap)
 _tables_lock = threading.Lock()
 
 
@@ -56,6 +57,21 @@ def _need_cuda_f32(name, t, dtype=torch.float32, local=True):
         raise ValueError("%s lives on %s but the current CUDA device is %d; call torch.cuda.set_device(%d) "
                          "(one process per GPU) or wrap the call in torch.cuda.device(...)"
                          % (name, t.device, torch.cuda.current_device(), t.device.index))
+
+
+def _need_frame_phase(frame_phase, B, nF):
+    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    if tuple(frame_phase.shape) != (B, nF) or not frame_phase.is_contiguous():
+        raise ValueError("frame_phase must be a contiguous [%d, %d] tensor (phase_scan of the same f0), got %s"
+                         % (B, nF, tuple(frame_phase.shape)))
+
+
+def _noise_rows(noise_in, B, T):
+    """explicit noise samples for B utterances of T samples -> contiguous [B, T]"""
+    _need_cuda_f32("noise_in", noise_in)
+    if noise_in.numel() != B * T:
+        raise ValueError("noise must hold B*T = %d*%d samples, got %s" % (B, T, tuple(noise_in.shape)))
+    return noise_in.reshape(B, T).contiguous()
 
 
 def _frames_2d(f0_frames):
@@ -120,7 +136,7 @@ def phase_scan(f0_frames, block, sampling_rate, initial_phase=None, infer=True):
 def sins_bank(f0_frames, frame_phase, c_amp, block, sampling_rate, infer=True):
     f0 = _frames_2d(f0_frames)
     B, nF = f0.shape
-    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    _need_frame_phase(frame_phase, B, nF)
     c, stride = _ctrl_view("amplitudes", c_amp, B, nF)
     out = torch.empty(B, nF * block, dtype=torch.float32, device=f0.device)
     rc = _lib.lib().b2d_sins_bank(f0.data_ptr(), frame_phase.data_ptr(), c.data_ptr(), stride, B, nF, int(block),
@@ -155,6 +171,9 @@ def ltv_fir(x, ir, block, seed=0, utterance_offset=0, generic=False):
         if x.shape[0] != B:
             raise ValueError("Batch size of audio ({}) and impulse response ({}) must be the same."
                              .format(x.shape[0], B))
+        if x.dim() != 2 or x.shape[1] != nF * int(block):
+            raise ValueError("audio must be [B, n_frames*block] = [%d, %d], got %s (the reference derives the hop "
+                             "from the lengths, ddsp/core.py:156; here block is explicit)" % (B, nF * int(block), tuple(x.shape)))
         x = x.contiguous()
     y = torch.empty(B, nF * block, dtype=torch.float32, device=ir.device)
     Lh = _lib.lib()
@@ -176,7 +195,7 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
     waveform straight over NVLink."""
     f0 = _frames_2d(f0_frames)
     B, nF = f0.shape
-    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    _need_frame_phase(frame_phase, B, nF)
     ca, s0 = _ctrl_view("amplitudes", c_amp, B, nF)
     cg, s1 = _ctrl_view("group_delay", c_group_delay, B, nF)
     cn, s2 = _ctrl_view("noise_magnitude", c_noise, B, nF)
@@ -189,8 +208,7 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
     dev = f0.device
     T = nF * block
     if noise_in is not None:
-        _need_cuda_f32("noise_in", noise_in)
-        noise_in = noise_in.reshape(B, T).contiguous()
+        noise_in = _noise_rows(noise_in, B, T)
     L = _lib.lib()
     ws_bytes = L.b2d_sins_workspace_bytes(B, nF, int(block), Ma, Mn)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -209,7 +227,8 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
                           int(block), H, Ma, Mn, float(sampling_rate), 0 if infer else 1, signal.data_ptr(),
                           _ptr(harmonic), _ptr(noise), ws.data_ptr(), ws_bytes, _stream())
     _lib.check(rc, "b2d_sins_synth")
-    _count(4 if Ma == Mn else 5)
+    nsplit = max(1, min(abs(_overlap_mode), B)) if abs(_overlap_mode) >= 2 else 1
+    _count(2 + nsplit * (2 if Ma == Mn else 3))
     return signal, harmonic, noise
 
 
@@ -242,7 +261,7 @@ def sinegen(f0, upp, sampling_rate, dim, rand_ini, sine_amp=0.1, noise_std=0.003
 def comb_source(f0_frames, frame_phase, block, sampling_rate, infer=True):
     f0 = _frames_2d(f0_frames)
     B, nF = f0.shape
-    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    _need_frame_phase(frame_phase, B, nF)
     out = torch.empty(B, nF * block, dtype=torch.float32, device=f0.device)
     rc = _lib.lib().b2d_comb_source(f0.data_ptr(), frame_phase.data_ptr(), B, nF, int(block), float(sampling_rate),
                                     0 if infer else 1, out.data_ptr(), _stream())
@@ -266,14 +285,13 @@ def combsub_synth(f0_frames, frame_phase, c_group_delay, c_harmonic, c_noise, bl
     """Whole old-CombSub DSP after Unit2Control -> (signal, harmonic, noise) [B, T] each."""
     f0 = _frames_2d(f0_frames)
     B, nF = f0.shape
-    _need_cuda_f32("frame_phase", frame_phase, torch.float64)
+    _need_frame_phase(frame_phase, B, nF)
     (cg, ch, cn), stride = _same_stride([("group_delay", c_group_delay), ("harmonic_magnitude", c_harmonic),
                                          ("noise_magnitude", c_noise)], B, nF)
     Ma, Mh, Mn = cg.shape[2], ch.shape[2], cn.shape[2]
     dev, T = f0.device, nF * block
     if noise_in is not None:
-        _need_cuda_f32("noise_in", noise_in)
-        noise_in = noise_in.reshape(B, T).contiguous()
+        noise_in = _noise_rows(noise_in, B, T)
     L = _lib.lib()
     ws_bytes = L.b2d_combsub_workspace_bytes(B, nF, int(block), Ma, Mh, Mn)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -309,15 +327,19 @@ def superfast_scan(f0_frames, block, sampling_rate):
 
 def superfast_synth(ws, c_hm, c_hp, c_nm, c_np, block, win_length, noise_in=None, seed=0, utterance_offset=0,
                     signal_out=None):
+    if c_hm.dim() != 3:
+        raise ValueError("controls must be [B, n_frames, win_length/2+1]")
     B, nF = c_hm.shape[0], c_hm.shape[1]
+    if not isinstance(ws, torch.Tensor) or not ws.is_cuda or ws.dtype != torch.uint8 or \
+            ws.numel() < _lib.lib().b2d_superfast_workspace_bytes(B, nF):
+        raise ValueError("ws must be the workspace superfast_scan returned for the same (B, n_frames) = (%d, %d)" % (B, nF))
     (hm, hp, nm, npz), stride = _same_stride([("harmonic_magnitude", c_hm), ("harmonic_phase", c_hp),
                                               ("noise_magnitude", c_nm), ("noise_phase", c_np)], B, nF)
     if hm.shape[2] != win_length // 2 + 1:
         raise ValueError("controls must have win_length/2+1 = %d bins" % (win_length // 2 + 1))
     T = nF * block
     if noise_in is not None:
-        _need_cuda_f32("noise_in", noise_in)
-        noise_in = noise_in.reshape(B, T).contiguous()
+        noise_in = _noise_rows(noise_in, B, T)
     if signal_out is not None:
         _need_cuda_f32("signal_out", signal_out, local=False)        # may be peer-mapped memory of another GPU
         if tuple(signal_out.shape) != (B, T) or not signal_out.is_contiguous():
@@ -369,6 +391,8 @@ def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utt
     """CombSubFast after the source: comb [B, T] + raw controls [B, nF, block+1] -> signal [B, T]
     (reference ddsp/vocoder.py:758-784)."""
     _need_cuda_f32("comb", comb)
+    if comb.dim() != 2 or comb.shape[1] % int(block) != 0:
+        raise ValueError("comb must be [B, n_frames*block] with block=%d, got %s" % (block, tuple(comb.shape)))
     B, T = comb.shape
     nF = T // block
     (hm, hp, nm), stride = _same_stride([("harmonic_magnitude", c_hm), ("harmonic_phase", c_hp),
@@ -377,8 +401,7 @@ def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utt
         raise ValueError("controls must have block_size+1 = %d bins" % (block + 1))
     comb = comb.contiguous()
     if noise_in is not None:
-        _need_cuda_f32("noise_in", noise_in)
-        noise_in = noise_in.reshape(B, T).contiguous()
+        noise_in = _noise_rows(noise_in, B, T)
     signal = torch.empty(B, T, dtype=torch.float32, device=comb.device)
     rc = _lib.lib().b2d_combsubfast_filter(comb.data_ptr(), hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), stride,
                                            _ptr(noise_in), int(seed), int(utterance_offset), B, nF, int(block),
@@ -391,3 +414,11 @@ def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utt
 def set_fft_arith(name):
     """'scalar' (default) | 'packed' (f32x2 complex additions in the FFT kernels; experimental, not yet run on hardware)."""
     _lib.check(_lib.lib().b2d_set_fft_arith({"scalar": 0, "packed": 1}[name]), "b2d_set_fft_arith")
+
+
+def set_overlap(mode):
+    """0 / False: every kernel of a synthesizer call in order on the current stream; 1 / True: impulse responses next to
+    the bank on an internal side stream; k >= 2: additionally k staggered sub-batches on two streams (b200ddsp.h)."""
+    global _overlap_mode
+    _lib.check(_lib.lib().b2d_set_overlap(int(mode)), "b2d_set_overlap")
+    _overlap_mode = int(mode)

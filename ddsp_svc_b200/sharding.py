@@ -165,18 +165,50 @@ class PeerGather:
             rows.record_stream(stream)
 
 
-def synthesize_and_push(synth_chunk, peer, n_local, device, chunks=4):
-    """Chunked synthesis; each finished chunk is DMA-copied into rank dst's peer-mapped buffer on a side
-    stream while the next chunk is being synthesized.  Returns the gathered tensor on dst after a
-    device barrier."""
+def synthesize_and_push(synth_chunk, peer, n_local, device, chunks=4, streams=1, direct=False):
+    """Chunked synthesis with the transfer of finished chunks to rank dst overlapped with the synthesis of the rest.
+
+    ``synth_chunk(lo, hi, signal_out=None)`` synthesizes local rows [lo, hi) on the current stream and returns the
+    [hi-lo, n_samples] waveform (written into ``signal_out`` when given).
+
+    * ``direct=False``: each finished chunk is DMA-copied (copy engine, no SM) into rank dst's peer-mapped buffer on a
+      side stream while the next chunk computes;
+    * ``direct=True``: the chunk's last kernel stores the waveform straight into rank dst's buffer (peer stores over
+      NVLink); with ``streams`` > 1 the back-pressured stores of chunk c overlap the arithmetic of chunk c+1.
+    * ``streams`` > 1: consecutive chunks run on alternating compute streams, so chunk c+1's first kernels fill the SMs
+      that chunk c's last wave leaves idle (and waveforms leave the GPU spread over the step, not at its end).
+
+    Returns the gathered tensor on dst after a device-side barrier (stream ordered on the current stream)."""
     main = torch.cuda.current_stream(device)
     comm = _comm_stream(device)
     comm.wait_stream(main)
-    for lo, hi in _chunk_bounds(n_local, chunks):
-        part = synth_chunk(lo, hi)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        comm.wait_event(ev)
-        peer.push_rows(lo, hi, part, comm)
+    side = _compute_streams(device, streams) if streams > 1 else []
+    for s in side:
+        s.wait_stream(main)
+    for c, (lo, hi) in enumerate(_chunk_bounds(n_local, chunks)):
+        cs = side[c % len(side)] if side else main
+        with torch.cuda.stream(cs):
+            if direct:
+                part = synth_chunk(lo, hi, signal_out=peer.my_rows[lo:hi])
+            else:
+                part = synth_chunk(lo, hi)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                comm.wait_event(ev)
+                peer.push_rows(lo, hi, part, comm)
+            del part
+    for s in side:
+        main.wait_stream(s)
     main.wait_stream(comm)
     return peer.finish()
+
+
+_compute = {}
+
+
+def _compute_streams(device, n):
+    key = torch.device(device).index
+    have = _compute.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:n]

@@ -9,7 +9,9 @@ class SineGen(torch.nn.Module):
     """SineGen(samp_rate, harmonic_num=0, sine_amp=0.1, noise_std=0.003, voiced_threshold=0)
 
     forward(f0 [B, n_frames], upp) -> [B, n_frames*upp, harmonic_num+1].  No parameters or
-    buffers, like the reference.  The random initial phases are drawn with torch.rand on the
+    buffers, like the reference.  Seeding contract: the in-kernel Philox stream is keyed by one 62-bit seed drawn per
+    forward from torch's CPU generator (``torch.manual_seed`` makes runs reproducible; ``torch.cuda.manual_seed`` has no
+    effect) -- drawing it on the host keeps the call free of device syncs.  The random initial phases are drawn with torch.rand on the
     input's device exactly like the reference (models.py:144); the additive Gaussian noise comes
     from the in-kernel Philox generator unless ``noise`` is given.
     """
@@ -46,6 +48,19 @@ class SourceModuleHnNSF(torch.nn.Module):
         self.l_sin_gen = SineGen(sampling_rate, harmonic_num, sine_amp, add_noise_std, voiced_threshod)
         self.l_linear = torch.nn.Linear(harmonic_num + 1, 1)
         self.l_tanh = torch.nn.Tanh()
+        self.__dict__["_bias_cache"] = None
+
+    def _bias(self):
+        """The Linear bias as a host float for the kernel's scalar argument.  Read back from the device only when the
+        parameter changed (in-place version counter / storage), not on every forward: no per-call device sync, and the
+        forward stays capturable in a CUDA graph once warmed up."""
+        b = self.l_linear.bias
+        key = (b._version, b.data_ptr())
+        c = self.__dict__.get("_bias_cache")
+        if c is None or c[0] != key:
+            c = (key, float(b.detach().reshape(-1)[0]))
+            self.__dict__["_bias_cache"] = c
+        return c[1]
 
     def forward(self, x, upp, rand_ini=None, noise=None, utterance_offset=0):
         g = self.l_sin_gen
@@ -55,6 +70,6 @@ class SourceModuleHnNSF(torch.nn.Module):
             rand_ini = torch.rand(1, 1, g.dim, device=x.device)
             rand_ini[..., 0] = 0
         return ops.source_module(x, int(upp), g.sampling_rate, g.dim, rand_ini, self.l_linear.weight,
-                                 float(self.l_linear.bias.detach().reshape(-1)[0]), g.sine_amp, g.noise_std,
+                                 self._bias(), g.sine_amp, g.noise_std,
                                  g.voiced_threshold, noise_in=noise, seed=0 if noise is not None else _host_seed(),
                                  utterance_offset=utterance_offset)

@@ -35,6 +35,13 @@ def _host_seed():
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
+def _check_shape(cls, ok, what):
+    """Shapes the kernels do not cover fail when the model is BUILT (load_model / patch_reference time), not at the
+    first forward after some kernels have already been launched."""
+    if not ok:
+        raise ValueError("%s on B200: %s (every config the reference ships uses block_size 512)" % (cls, what))
+
+
 class _SynthBase(torch.nn.Module):
     def _scalars(self):
         """sampling_rate / block_size live in 0-dim buffers (state-dict compatible with the
@@ -63,6 +70,10 @@ class Sins(_SynthBase):
     def __init__(self, sampling_rate, block_size, n_harmonics, n_mag_allpass, n_mag_noise, n_unit=256, n_spk=1,
                  unit2ctrl=None):
         super().__init__()
+        _check_shape("Sins", int(block_size) % 256 == 0 and 0 < int(block_size) <= 2048, "block_size %s must be a "
+                     "multiple of 256 up to 2048" % (block_size,))
+        _check_shape("Sins", 0 < int(n_harmonics) <= 512 and min(int(n_mag_allpass), int(n_mag_noise)) >= 2 and
+                     max(int(n_mag_allpass), int(n_mag_noise)) <= 1025, "n_harmonics <= 512 and 2 <= n_mag <= 1025")
         self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
         self.register_buffer("block_size", torch.tensor(block_size))
         split_map = {
@@ -95,6 +106,10 @@ class CombSub(_SynthBase):
     def __init__(self, sampling_rate, block_size, n_mag_allpass, n_mag_harmonic, n_mag_noise, n_unit=256, n_spk=1,
                  unit2ctrl=None):
         super().__init__()
+        _check_shape("CombSub", int(block_size) % 256 == 0 and 0 < int(block_size) <= 2048, "block_size %s must be a "
+                     "multiple of 256 up to 2048" % (block_size,))
+        _check_shape("CombSub", min(int(n_mag_allpass), int(n_mag_harmonic), int(n_mag_noise)) >= 2 and
+                     max(int(n_mag_allpass), int(n_mag_harmonic), int(n_mag_noise)) <= 1025, "2 <= n_mag <= 1025")
         self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
         self.register_buffer("block_size", torch.tensor(block_size))
         split_map = {
@@ -126,6 +141,8 @@ class CombSubSuperFast(_SynthBase):
     def __init__(self, sampling_rate, block_size, win_length, n_unit=256, n_spk=1, use_pitch_aug=False,
                  pcmer_norm=False, unit2ctrl=None):
         super().__init__()
+        _check_shape("CombSubSuperFast", int(block_size) == 512 and int(win_length) == 2048,
+                     "only block_size 512 / win_length 2048 (configs/combsub.yaml) is built, got %s / %s" % (block_size, win_length))
         self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
         self.register_buffer("block_size", torch.tensor(block_size))
         self.register_buffer("win_length", torch.tensor(win_length))
@@ -170,6 +187,7 @@ class CombSubFast(_SynthBase):
     def __init__(self, sampling_rate, block_size, n_unit=256, n_spk=1, use_pitch_aug=False, pcmer_norm=False,
                  unit2ctrl=None):
         super().__init__()
+        _check_shape("CombSubFast", int(block_size) == 512, "only block_size 512 is built, got %s" % (block_size,))
         self.register_buffer("sampling_rate", torch.tensor(sampling_rate))
         self.register_buffer("block_size", torch.tensor(block_size))
         self.register_buffer("window", torch.sqrt(torch.hann_window(2 * block_size)))

@@ -11,10 +11,16 @@
  * Conventions
  *  - plain C types only; every pointer is a DEVICE pointer to contiguous fp32 data unless
  *    stated otherwise; `stream` is a cudaStream_t passed as void*.
- *  - the library never allocates or frees device memory, never synchronises the stream
- *    and keeps no mutable global state (thread-local last-error string only), so it is
- *    re-entrant from any host thread (the reference is called from the audio-callback
- *    thread of gui.py:376-414 and from Flask).
+ *  - the library never allocates or frees device memory and never synchronises the stream.
+ *    Its entry points are re-entrant from any host thread (the reference is called from the
+ *    audio-callback thread of gui.py:376-414 and from Flask): the last-error string is
+ *    thread-local, and the only process-wide state is (i) a mutex-protected, per-device
+ *    cache of internal fork/join streams and events (b2d_sins_synth runs independent
+ *    kernels side by side and joins them on the caller's stream before returning) and
+ *    (ii) the b2d_set_* implementation selectors: atomics, each read ONCE at the top of a
+ *    call.  The selectors exist for A/B measurements and tests; every setting computes the
+ *    same function, so flipping one from another thread changes which kernel a later call
+ *    uses, never a result.
  *  - return value: 0 = ok, <0 = argument error (B2D_ERR_*), >0 = cudaError_t of the failed
  *    launch.  No exceptions or aborts cross the ABI.  b2d_last_error() describes the last
  *    failure on the calling thread.
@@ -234,6 +240,15 @@ int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude,
  * instructions in the FIR / SuperFast main loops by SASS count).  EXPERIMENTAL: builds, not yet run on hardware.
  * Process-wide test/diagnostic knob. */
 int b2d_set_fft_arith(int packed);
+
+/* How b2d_sins_synth overlaps its independent kernels on an internal side stream that is joined on the caller's stream
+ * before the call returns (event record/wait only; legal under stream capture).  0: every kernel on the caller's
+ * stream, in order.  1: impulse-response builds next to the oscillator bank.  k >= 2: additionally the batch is cut into
+ * k sub-batches that alternate between the two streams, staggered, so the FIR of one shares the SMs with the bank of the
+ * next (-k: the same with a high-priority side stream).  Same results in every mode (the noise is keyed by the global
+ * utterance index, the FFT-domain FIR is bit-identical for any batch split).  Process-wide test/diagnostic knob (atomic,
+ * read once per call). */
+int b2d_set_overlap(int mode);
 
 /* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto, 1 one sample per
  * thread (first kernel of round 1; also the only one for dim other than 1 or 9), 2 four samples per thread (auto),

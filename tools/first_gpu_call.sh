@@ -8,8 +8,9 @@ export B2D_EXPERIMENTAL=1            # also run the variants that have not execu
 timeout 120 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu_experimental.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu_experimental.log; tail -3 gpurun_out/pytest_gpu_experimental.log
 unset B2D_EXPERIMENTAL
-b() { name=$1; shift; timeout 90 python bench.py --steps 10 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/b_$name.json 2> gpurun_out/b_$name.err; }
+b() { name=$1; shift; timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ${NO_OTHERS:+--no-others} "$@" > gpurun_out/b_$name.json 2> gpurun_out/b_$name.err; }
 b sins_default
+export NO_OTHERS=1
 b sins_packed --fft-arith packed
 b sins_direct --fir-impl cuda
 b sins_2streams --e2e-streams 2
