@@ -27,7 +27,10 @@ SR, P = 44100, 512
 OTHER_WORKLOADS = ("sins_cfg1", "combsub", "superfast", "combsubfast", "sinegen", "srcmod")
 
 # N -> (gather mode, chunks, compute streams) chosen by `--gather auto` (measured on B200)
-AUTO_GATHER = {2: ("peer", 1, 1), 4: ("peer", 1, 1), 8: ("peer-copy", 4, 2)}
+# round 2, ms/step at N=8 with 0.84 ms of kernels (profiles/r2_scale_m8_*.json): peer stores 1.077 | per-chunk peer stores
+# 4 chunks x 2 streams 1.069 | copy-engine push 2.42-2.49 | NCCL gather 1.425 | no gather 0.848.  The 7 x 56.4 MB
+# arrive while the FIR kernel (0.375 ms) runs: 395 MB / (0.375 + 0.23 ms exposed) = 653 GB/s into rank 0.
+AUTO_GATHER = {2: ("peer", 1, 1), 4: ("peer", 1, 1), 8: ("peer", 1, 1)}
 
 WORKLOADS = {
     # name: (kind, batch per GPU, seconds, params, algorithmic bytes per output sample)
@@ -151,9 +154,9 @@ class ClockSampler:
 
 def ncu_traffic(workload, kernel_label):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    ncu --set full capture (profiles/r1_traffic.json); None when no capture is recorded for it."""
+    ncu --set full capture (profiles/r2_traffic.json); None when no capture is recorded for it."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             ent = json.load(f).get(workload, {})
         return ent.get("dram_bytes_per_launch") if ent.get("bench_kernel") == kernel_label else None
     except Exception:

@@ -1,6 +1,7 @@
 // C-ABI plumbing of libb200ddsp: version, thread-local error string, and the drivers that
 // chain the kernels of one synthesizer on the caller's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "b2d_common.cuh"
@@ -28,7 +29,14 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 }  // namespace b2d
 
-namespace b2d { std::atomic<int> g_fft_packed{0}; }
+namespace b2d {
+// B2D_FFT_ARITH=packed|scalar in the environment picks the initial value (whole-suite A/B runs); b2d_set_fft_arith overrides
+static int fft_arith_default() {
+    const char* e = getenv("B2D_FFT_ARITH");
+    return (e && !strcmp(e, "packed")) ? 1 : 0;
+}
+std::atomic<int> g_fft_packed{fft_arith_default()};
+}
 
 // ---------------------------------------------------------------------------------------
 // Fork/join inside one synthesizer call.  The impulse-response builds depend only on the raw controls, the oscillator

@@ -4,14 +4,25 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The reference is a Python /
 PyTorch program; its hot path (ddsp/vocoder.py, ddsp/core.py,
 nsf_hifigan/models.py) imports several third-party packages that are not
 installed here and are not used by the path.  They are replaced by empty stub
-modules before import.  /root/reference exists only in the build container, so
-callers must check ``available()`` first.
+modules before import.  /root/reference exists only in the build container; on the
+GPU box the staged copy under baseline/_ref/ (tools/stage_reference.py) is used when
+present, so callers must check ``available()`` first.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DDSP_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """The live checkout in the build container, else the staged copy that travels to the GPU box
+    (baseline/_ref/, written by tools/stage_reference.py; git-ignored)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("DDSP_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "ddsp", "vocoder.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUBS = ("pyworld", "parselmouth", "torchcrepe", "resampy", "fairseq", "gin",
           "local_attention")

@@ -78,6 +78,40 @@ def test_combsub_vs_float64_truth():
     assert e_gpu < 1e-6
 
 
+def test_combsub_full_size_config3b():
+    """BASELINE config 3b shape (old CombSub, B=32 x 10 s, n_mag 256/512/256): finite, signal == harmonic + noise, the
+    1022-tap FFT-domain FIR (2048-point instance) equals the one-thread-per-sample FIR on the same data, and two sampled
+    utterances agree with the oracle port."""
+    from oracle import torch_port as tp
+    B, nF = 32, 861
+    sm = syn.combsub_split_map(256, 512, 256)
+    f0 = syn.make_f0(B, nF, SR, P)
+    dense, ctrls = syn.make_ctrl(B, nF, sm)
+    noise = syn.uniform_noise(B, nF * P, 21)
+    dc = syn.split_views(dense.to(DEV), sm)
+    f0d = f0.to(DEV)
+    fp, _ = ops.phase_scan(f0d, P, SR)
+    sig, harm, nz = ops.combsub_synth(f0d, fp, dc["group_delay"], dc["harmonic_magnitude"], dc["noise_magnitude"], P, SR,
+                                      noise_in=noise.to(DEV))
+    assert torch.isfinite(sig).all()
+    assert torch.equal(sig, harm + nz)
+    # the 2048-point FFT-domain instance at full size against the generic kernel (first 4 utterances: the generic
+    # kernel is one thread per output sample x 1022 taps)
+    comb = ops.comb_source(f0d, fp, P, SR)
+    ir_h = ops.ir_build(dc["harmonic_magnitude"], ops.IR_MAG_DYNAMIC, SR, f0_frames=f0d)
+    y_f = ops.ltv_fir(comb[:4], ir_h[:4], P)
+    y_g = ops.ltv_fir(comb[:4], ir_h[:4], P, generic=True)
+    e_fg = (y_f - y_g).abs().max().item()
+    worst = 0.0
+    for r in (3, 30):
+        with torch.no_grad():
+            ref = tp.combsub_forward(f0[r:r + 1], {k: v[r:r + 1] for k, v in ctrls.items()}, SR, P, noise=noise[r:r + 1])
+        worst = max(worst, util.rms(sig[r:r + 1].cpu() - ref["signal"]))
+    report.record("combsub_full", fft_vs_generic_max=e_fg, row_rms=worst, signal_rms=sig.pow(2).mean().sqrt().item())
+    assert e_fg < 2e-6
+    assert worst < GATE_RMS
+
+
 @pytest.mark.parametrize("name", [n for n, c in G.CASES.items() if c["kind"] == "sinegen"])
 def test_sinegen_matches_reference_golden(name):
     inp = G.build_inputs(name)

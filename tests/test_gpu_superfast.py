@@ -92,3 +92,29 @@ def test_superfast_in_kernel_noise_and_full_size():
                             d8["noise_phase"], P, 2048, seed=3, utterance_offset=8)
     assert torch.equal(a[8:], c)
     report.record("superfast_full", rms=a.pow(2).mean().sqrt().item())
+
+
+def test_superfast_full_size_sampled_rows_match_oracle():
+    """BASELINE config 3 shape with explicit noise: two sampled utterances of the B=32 x 10 s batch against the
+    oracle port (the whole batch is too slow for the CPU oracle in seconds), as tests/test_gpu_sins.py does for Sins."""
+    from oracle import torch_port as tp
+    B, nF = 32, 861
+    sm = syn.superfast_split_map(2048)
+    f0 = syn.make_f0(B, nF, SR, P, unvoiced_fraction=0.03)
+    dense, ctrls = syn.make_ctrl(B, nF, sm)
+    rows = (5, 29)
+    noise = torch.zeros(B, nF * P)
+    for r in rows:
+        noise[r] = syn.normal_noise((1, nF * P), 100 + r)[0]
+    ws, _ = ops.superfast_scan(f0.to(DEV), P, SR)
+    dc = syn.split_views(dense.to(DEV), sm)
+    sig = ops.superfast_synth(ws, dc["harmonic_magnitude"], dc["harmonic_phase"], dc["noise_magnitude"],
+                              dc["noise_phase"], P, 2048, noise_in=noise.to(DEV))
+    assert torch.isfinite(sig).all()
+    for r in rows:
+        with torch.no_grad():
+            ref = tp.superfast_forward(f0[r:r + 1], {k: v[r:r + 1] for k, v in ctrls.items()}, SR, P, 2048,
+                                       noise=noise[r:r + 1])
+        e = util.rms(sig[r:r + 1].cpu() - ref["signal"])
+        report.record("superfast_full_row%d" % r, err=e, rms=util.rms(ref["signal"]))
+        assert e < GATE_RMS
