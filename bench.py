@@ -471,18 +471,39 @@ def eager_gpu_baseline(w, run, flush, torch, reps=3):
         f0, ctrls = run.f0_d, None
     else:
         f0, ctrls = run.f0_d, run.ctrl_d
-    oracle_forward(w, f0[:2], {k: v[:2] for k, v in ctrls.items()} if ctrls else None)     # cuFFT plans, allocator
+    kind, what = "port", "oracle port of the reference (same ATen operators)"
+    fwd = lambda f, c: oracle_forward(w, f, c)
+    if w["kind"] == "sins":
+        try:                                   # the unmodified reference class when its sources travelled (baseline/_ref)
+            import contextlib, io
+            from oracle import ref_loader
+            if ref_loader.available():
+                with contextlib.redirect_stdout(io.StringIO()):
+                    V = ref_loader.load()[0]
+                    ref = V.Sins(SR, P, w["H"], w["Ma"], w["Mn"], n_unit=8, n_spk=1).to(run.dev).eval()
+
+                class Fixed(torch.nn.Module):
+                    def forward(self, *a, **k):
+                        return self.c, None
+                ref.unit2ctrl = Fixed()
+
+                def fwd(f, c):                 # noqa: F811 -- Sins.forward of the reference, DSP only (controls preset)
+                    ref.unit2ctrl.c = c
+                    return ref(None, f, None)
+                kind, what = "reference", "the reference's own ddsp.vocoder.Sins.forward (unmodified sources staged under baseline/_ref, Unit2Control replaced by preset controls)"
+        except Exception as e:                 # fall back to the port, say why
+            what += " [reference classes unavailable: %s]" % (str(e).splitlines()[0][:80] if str(e) else type(e).__name__)
+    fwd(f0[:2], {k: v[:2] for k, v in ctrls.items()} if ctrls else None)     # cuFFT plans, allocator
     ts = []
     for _ in range(reps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); oracle_forward(w, f0, ctrls); b.record(); b.synchronize()
+        a.record(); fwd(f0, ctrls); b.record(); b.synchronize()
         ts.append(a.elapsed_time(b))
     torch.cuda.empty_cache()
     ms = min(ts)
-    return {"value": w["B"] * run.T / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "kind": "port",
-            "what": "oracle port of the reference (same ATen operators) run eagerly on this GPU, full batch, "
-                    "inputs resident in HBM, best of %d" % reps}
+    return {"value": w["B"] * run.T / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "kind": kind,
+            "what": what + " run eagerly on this GPU, full batch, inputs resident in HBM, best of %d" % reps}
 
 
 def main():
@@ -514,7 +535,7 @@ def main():
                     help="compute streams of the host-buffer pipeline (HostPipeline(compute_streams=...); >1 not yet measured)")
     ap.add_argument("--fir-impl", default="auto", choices=["auto", "cuda", "tc", "cuda8", "fft"],
                     help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
-    ap.add_argument("--fft-arith", default="scalar", choices=["scalar", "packed"],
+    ap.add_argument("--fft-arith", default="packed", choices=["scalar", "packed"],
                     help="A/B switch: packed f32x2 complex additions in the FFT kernels (ops.set_fft_arith)")
     ap.add_argument("--overlap", type=int, default=None,
                     help="A/B switch (ops.set_overlap): 0 in order, 1 impulse responses beside the bank, k >= 2 "
@@ -552,7 +573,7 @@ def main():
         run.ops.set_fir_impl(args.fir_impl)
     if args.overlap is not None:
         run.ops.set_overlap(args.overlap)
-    if args.fft_arith != "scalar":
+    if args.fft_arith != "packed":
         run.ops.set_fft_arith(args.fft_arith)
     B, nF, T = run.B, run.nF, run.T
     do_gather = world > 1 and not args.no_gather

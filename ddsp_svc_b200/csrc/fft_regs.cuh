@@ -79,4 +79,25 @@ template <int R, bool PK> struct Dft {
     }
 };
 
+// 16-point DFT whose inputs 8..15 are zero (the first pass of a transform whose upper half is zero padding):
+//   X[2m] = DFT8(v[r])[m],  X[2m+1] = DFT8(v[r] W16^r)[m]     (decimation in frequency with v[r + 8] = 0)
+// -- the 16 closing additions of the full butterfly disappear.  Reads v[0..7], writes v[0..15] in natural order.
+template <bool PK> struct Dft16ZeroUpper {
+    static __device__ __forceinline__ void run(float2* v) {
+        float2 e[8], o[8];
+        e[0] = v[0]; o[0] = v[0];
+        e[1] = v[1]; o[1] = twid<16, 1>(v[1]);
+        e[2] = v[2]; o[2] = twid<16, 2>(v[2]);
+        e[3] = v[3]; o[3] = twid<16, 3>(v[3]);
+        e[4] = v[4]; o[4] = twid<16, 4>(v[4]);
+        e[5] = v[5]; o[5] = twid<16, 5>(v[5]);
+        e[6] = v[6]; o[6] = twid<16, 6>(v[6]);
+        e[7] = v[7]; o[7] = twid<16, 7>(v[7]);
+        Dft<8, PK>::run(e);
+        Dft<8, PK>::run(o);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { v[2 * m] = e[m]; v[2 * m + 1] = o[m]; }
+    }
+};
+
 }  // namespace b2d_fft

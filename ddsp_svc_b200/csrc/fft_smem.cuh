@@ -30,8 +30,11 @@ template <int N> struct Plan {
 // thread otherwise.  A stage reads, hits a barrier, then writes; different stages touch different transforms, so stage
 // s+1 may start reading while other threads still write stage s, and only one stage's butterflies are live per thread.
 // Barriers per pass: stages + 1.
-template <int N, int R, int NS, int TW, int NBATCH, bool PK = false>
+// ZU (first pass only: R = 16, NS = 1): the upper half of every transform is zero padding and is neither read nor
+// required to be initialised -- half the loads, no zero fill, pruned butterfly (Dft16ZeroUpper).
+template <int N, int R, int NS, int TW, int NBATCH, bool PK = false, bool ZU = false>
 __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__ tw, int tid) {
+    static_assert(!ZU || (R == 16 && NS == 1 && TW == 0), "zero-upper pruning applies to the first radix-16 pass");
     constexpr int NB = N / R;                                        // butterflies per FFT
     constexpr int PER = NB > kThreads ? NB / kThreads : 1;           // butterflies per thread and stage
     constexpr int FPS = NB >= kThreads ? 1 : kThreads / NB;          // FFTs per stage
@@ -51,7 +54,7 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
             if (active[u]) {
                 const float2* fft = buf + g * kPad;
 #pragma unroll
-                for (int r = 0; r < R; ++r) v[u][r] = fft[padi(j + r * NB)];
+                for (int r = 0; r < (ZU ? R / 2 : R); ++r) v[u][r] = fft[padi(j + r * NB)];
                 if (TW == 1) {
 #pragma unroll
                     for (int r = 1; r < R; ++r) v[u][r] = cmul(v[u][r], tw[(r - 1) * NS + k]);
@@ -63,7 +66,8 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
                     v[u][4] = cmul(v[u][4], w4); v[u][5] = cmul(v[u][5], w5); v[u][6] = cmul(v[u][6], w6);
                     v[u][7] = cmul(v[u][7], w7);
                 }
-                Dft<R, PK>::run(v[u]);
+                if (ZU) Dft16ZeroUpper<PK>::run(v[u]);
+                else Dft<R, PK>::run(v[u]);
             }
         }
         __syncthreads();
@@ -82,10 +86,10 @@ __device__ __forceinline__ void fft_pass(float2* buf, const float2* __restrict__
 }
 
 // forward FFT of NBATCH transforms at buf, buf + kPad, ...
-template <int N, int NBATCH, bool PK = false>
+template <int N, int NBATCH, bool PK = false, bool ZU = false>
 __device__ __forceinline__ void fft_forward(float2* buf, const float2* tw2, const float2* tw3, int tid) {
     constexpr int R2 = Plan<N>::kR2;
-    fft_pass<N, 16, 1, 0, NBATCH, PK>(buf, nullptr, tid);
+    fft_pass<N, 16, 1, 0, NBATCH, PK, ZU>(buf, nullptr, tid);
     fft_pass<N, R2, 16, 1, NBATCH, PK>(buf, tw2, tid);
     fft_pass<N, 8, 16 * R2, 2, NBATCH, PK>(buf, tw3, tid);
 }

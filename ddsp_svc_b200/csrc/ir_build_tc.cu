@@ -77,6 +77,7 @@ struct IrTcParams {
     const float* f0;
     const float* image;      // tensor-core table image
     int n_total, M;
+    int rows;                // frames a CTA actually fills of its 128 TMEM lanes: 128, or 64 / 32 for small launches
     float hw_num;
     float* ir;
 };
@@ -94,7 +95,7 @@ struct IrTcParams {
 #else
 #define B2D_IR_TC_BOUNDS __launch_bounds__(kThreads, 1)
 #endif
-template <int MODE>
+template <int MODE, int ROWS>
 __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
     constexpr bool kAllpass = (MODE == B2D_IR_ALLPASS);
     constexpr int NACC = kAllpass ? 4 : 2;
@@ -110,7 +111,12 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int F0 = blockIdx.x * kRows;
+    // Small launches (one utterance of a real-time caller, a chunk of the host pipeline) are latency bound: a CTA then
+    // fills only `rows` of its 128 lanes -- the activations and the write-out scale with the rows, the MMAs do not care
+    // (a D row depends on its own A row only; the unused A rows are never written and their D rows never read).
+    constexpr int rows = ROWS, urows = ROWS >> 5;
+    static_assert(ROWS == 32 || ROWS == 64 || ROWS == 128, "rows per CTA");
+    const int F0 = blockIdx.x * rows;
     const float invL = 1.0f / (float)L;
     constexpr uint32_t kTmemCols = 512;
 
@@ -134,6 +140,18 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
 
     double run = 0.0;      // threads 0..127: group-delay cumsum of frame F0 + tid (fp64 accumulate, fp32 emit)
 
+    // raw controls of a chunk (element e = tid + 512 u -> row e >> 4, bin 16 ch + (e & 15)); fetched one chunk ahead so
+    // the global-load latency hides behind the previous chunk's barriers (it was the top stall of the first version)
+    float cpre[4];
+    auto fetch = [&](int ch) {
+#pragma unroll
+        for (int u = 0; u < urows; ++u) {
+            const int e = tid + u * kThreads, row = e >> 4, m = 16 * ch + (e & 15);
+            cpre[u] = (m < M && F0 + row < p.n_total) ? __ldg(p.c + (size_t)(F0 + row) * p.ctrl_stride + m) : 0.f;
+        }
+    };
+    fetch(0);
+
     for (int ch = 0; ch < NC; ++ch) {
         const int st = ch & 1;
         float* sA = stage0 + st * stage_floats;                    // A blocks: [kind][hi|lo][2][128][4]
@@ -156,15 +174,16 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
         if (kAllpass) {
             // phase 1: pi * tanh(c)   (:581)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < urows; ++u) {
                 const int e = tid + u * kThreads, row = e >> 4, i = e & 15, m = 16 * ch + i;
                 float g = 0.f;
-                if (m < M && F0 + row < p.n_total) g = B2D_PI_F * tanhf(__ldg(p.c + (size_t)(F0 + row) * p.ctrl_stride + m));
+                if (m < M && F0 + row < p.n_total) g = B2D_PI_F * tanhf(cpre[u]);
                 gds[row * 17 + i] = g;
             }
+            if (ch + 1 < NC) fetch(ch + 1);
             __syncthreads();
             // phase 2: running sum per frame, fp64 accumulate / fp32 emit   (:599, torch CPU cumsum)
-            if (tid < kRows) {
+            if (tid < rows) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     run += (double)gds[tid * 17 + i];
@@ -175,7 +194,7 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
         }
         // phase 3: spectrum values -> tf32 hi/lo -> A operand blocks
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < urows; ++u) {
             const int e = tid + u * kThreads, row = e >> 4, i = e & 15, m = 16 * ch + i;
             const bool act = (m < M) && (F0 + row < p.n_total);
             const float wgt = ((m == 0 || m == M - 1) ? 1.0f : 2.0f) * invL;
@@ -190,7 +209,7 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
                     r = cs * wgt; im = sn * wgt;
                 }
             } else if (act) {
-                float v = expf(__ldg(p.c + (size_t)(F0 + row) * p.ctrl_stride + m));
+                float v = expf(cpre[u]);
                 if (MODE == B2D_IR_MAG_HANN) v *= 0.0078125f;
                 r = v * wgt;
             }
@@ -208,6 +227,7 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
                 sA[((2 * par + 1) * 2 + 1) * kABlock + pos] = l;
             }
         }
+        if (!kAllpass && ch + 1 < NC) fetch(ch + 1);
         b2d::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -240,7 +260,7 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
     // ---- epilogue: warp (q, cg): TMEM lanes 32 q .. 32 q + 31, column blocks t0 = 16 (4 round + cg) ----
     const int q = warp & 3, cg = warp >> 2;
     const int row = 32 * q + lane;
-    const bool live = F0 + row < p.n_total;
+    const bool live = row < rows && F0 + row < p.n_total;
     float* stg = stage0;                                           // [cg][4 groups][128 rows][16], XOR-swizzled columns
     const uint32_t lane_base = tmem_d + ((uint32_t)(32 * q) << 16);
     float hw = 1.f;
@@ -258,7 +278,7 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
     const int nblk = Npad / 16;
     for (int rnd = 0; rnd * 4 < nblk; ++rnd) {
         const int blk = rnd * 4 + cg;
-        if (blk < nblk) {
+        if (blk < nblk && 32 * q < rows) {
             const int t0 = blk * 16;
             float Ce[16], Co[16], Se[16], So[16];
             if (kAllpass) {
@@ -287,20 +307,31 @@ __global__ void B2D_IR_TC_BOUNDS ir_build_tc_kernel(IrTcParams p) {
             }
         }
         __syncthreads();
-        // coalesced write-out: (cg, group, row) segments of 16 taps, one half-warp each
-        for (int seg = (tid >> 4); seg < 16 * kRows; seg += kThreads / 16) {
-            const int c2 = seg / (4 * kRows), rem = seg - c2 * (4 * kRows);
-            const int gI = rem / kRows, r2 = rem - gI * kRows;
-            const int blk2 = rnd * 4 + c2;
-            const int i = tid & 15;
-            const int tl = blk2 * 16 + i, th = M - 1 - tl;
-            if (blk2 >= nblk || F0 + r2 >= p.n_total || tl >= Nt) continue;
-            int idx; bool ok;
-            if (gI == 0) { idx = M - 1 + tl; ok = tl <= M - 2; }
-            else if (gI == 1) { idx = M - 1 - tl; ok = tl >= 1; }
-            else if (gI == 2) { idx = M - 1 + th; ok = th != tl && th <= M - 2; }
-            else { idx = tl; ok = th != tl && th >= 1; }
-            if (ok) p.ir[(size_t)(F0 + r2) * L + idx] = stg[c2 * (4 * kRows * 16) + (gI * kRows + r2) * 16 + (i ^ (r2 & 15))];
+        // coalesced write-out: a half-warp owns rows hw, hw + 32, ...; its 16 lanes are the 16 columns of a (column
+        // block, tap group) segment = 64 contiguous bytes of an IR row.  Everything that depends only on the column is
+        // hoisted out of the row loop (the first version decoded a flat segment index per element: ~25 instructions per
+        // 4-byte store, 44 M warp instructions per launch, 80 % of the kernel).
+        {
+            const int hw = tid >> 4, i = tid & 15;
+            const int swz = i ^ (hw & 15);                               // rows advance by 32: r2 & 15 == hw & 15
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                const int blk2 = rnd * 4 + c2;
+                const int tl = blk2 * 16 + i, th = M - 1 - tl;
+                if (blk2 < nblk && tl < Nt) {
+                    const int idx4[4] = {M - 1 + tl, M - 1 - tl, M - 1 + th, tl};
+                    const bool ok4[4] = {tl <= M - 2, tl >= 1, th != tl && th <= M - 2, th != tl && th >= 1};
+#pragma unroll
+                    for (int gI = 0; gI < 4; ++gI) {
+                        if (!ok4[gI]) continue;
+                        const float* src = stg + (c2 * 4 + gI) * (kRows * 16) + swz;
+                        float* dst = p.ir + (size_t)F0 * L + idx4[gI];
+#pragma unroll
+                        for (int r2 = hw; r2 < rows; r2 += 32)
+                            if (F0 + r2 < p.n_total) dst[(size_t)r2 * L] = src[r2 * 16];
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -342,10 +373,11 @@ int launch_tc(const IrTcParams& p, cudaStream_t st) {
     const size_t stage = (size_t)(NACC * 2 * kABlock + NACC * 2 * Npad * 8) * 4;
     if (2 * stage > (size_t)kStagingFloats * 4) return b2d::fail(B2D_ERR_UNSUPPORTED, "ir_build_tc: stages do not fit");
     const size_t smem = (size_t)kStagingFloats * 4 + (size_t)((L + 3) & ~3) * 4 + (size_t)kRows * 17 * 4 + 128;
-    auto kern = ir_build_tc_kernel<MODE>;
+    auto kern = p.rows == 32 ? ir_build_tc_kernel<MODE, 32> : p.rows == 64 ? ir_build_tc_kernel<MODE, 64>
+                                                                         : ir_build_tc_kernel<MODE, 128>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return b2d::fail((int)e, "ir_build_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e));
-    kern<<<(p.n_total + kRows - 1) / kRows, kThreads, smem, st>>>(p);
+    kern<<<(p.n_total + p.rows - 1) / p.rows, kThreads, smem, st>>>(p);
     return b2d::check_launch("ir_build_tc");
 }
 
@@ -374,6 +406,10 @@ int ir_build_tc_launch(const float* c, int64_t ctrl_stride, int mode, const floa
     IrTcParams p;
     p.c = c; p.ctrl_stride = ctrl_stride; p.f0 = f0; p.image = image;
     p.n_total = B * nF; p.M = M; p.hw_num = 1.5f * (float)sr; p.ir = ir;
+    // fewest rows per CTA that still run as a single wave of one CTA per SM; 128 once the grid fills the GPU anyway
+    p.rows = 128;
+    for (int r = 32; r < 128; r <<= 1)
+        if ((p.n_total + r - 1) / r <= 148) { p.rows = r; break; }
     switch (mode) {
         case B2D_IR_ALLPASS: return launch_tc<B2D_IR_ALLPASS>(p, st);
         case B2D_IR_MAG_HANN: return launch_tc<B2D_IR_MAG_HANN>(p, st);

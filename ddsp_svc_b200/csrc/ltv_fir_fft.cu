@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
         const float* ra = base + (size_t)min(max(fa, 0), nF - 1) * L;
         const float* rb = base + (size_t)min(max(fb, 0), nF - 1) * L;
         float2* buf = F + (2 * NJ + j) * kPad;
+        // taps L <= N/2: only the lower half of the buffer is written, the transform treats the upper half as zeros
 #pragma unroll
-        for (int u = 0; u < kN / kThreads; ++u) {
+        for (int u = 0; u < kN / 2 / kThreads; ++u) {
             const int tau = tid + u * kThreads;
             const bool in = tau < L;
             buf[padi(tau)] = make_float2(in ? __ldg(ra + tau) : 0.f, (in && with_b) ? __ldg(rb + tau) : 0.f);
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
         buf[padi(i0 + 2)] = make_float2(v.z, v.z * ((float)(i0 + 2) * s));
         buf[padi(i0 + 3)] = make_float2(v.w, v.w * ((float)(i0 + 3) * s));
 #pragma unroll
-        for (int z = kHop; z < kN; z += kHop)
+        for (int z = kHop; z < kN / 2; z += kHop)          // (N = 2048 only) zeros up to N/2; the upper half is implicit
 #pragma unroll
             for (int e = 0; e < 4; ++e) buf[padi(z + i0 + e)] = make_float2(0.f, 0.f);
     };
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
 #pragma unroll
     for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs - 1, gs, true);    // exactly the (h_{g+1}, h_{g+2}) pair of hops gs-2, gs-1
     __syncthreads();
-    fft_forward<N, NJ, PK>(F + 2 * NJ * kPad, tw2, tw3, tid);
+    fft_forward<N, NJ, PK, true>(F + 2 * NJ * kPad, tw2, tw3, tid);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const float2* H = F + (2 * NJ + j) * kPad;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
             load_ir_pair(j, g + 1, g + 2, true);
         }
         __syncthreads();
-        fft_forward<N, 3 * NJ, PK>(F, tw2, tw3, tid);
+        fft_forward<N, 3 * NJ, PK, true>(F, tw2, tw3, tid);      // all six have zero upper halves: pruned first pass
 
         // ---- Y_g = X_g H_g + XU_g (H_{g+1} - H_g),  Y_{g+1} = X_{g+1} H_{g+1} + XU_{g+1} (H_{g+2} - H_{g+1});
         //      paired as Y_g + j Y_{g+1} (Hermitian extension), stored re/im-swapped over XA(j) ----

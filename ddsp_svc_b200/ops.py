@@ -412,7 +412,7 @@ def combsubfast_filter(comb, c_hm, c_hp, c_nm, block, noise_in=None, seed=0, utt
 
 
 def set_fft_arith(name):
-    """'scalar' (default) | 'packed' (f32x2 complex additions in the FFT kernels; experimental, not yet run on hardware)."""
+    """'packed' (default: f32x2 complex additions in the FFT kernels) | 'scalar'."""
     _lib.check(_lib.lib().b2d_set_fft_arith({"scalar": 0, "packed": 1}[name]), "b2d_set_fft_arith")
 
 

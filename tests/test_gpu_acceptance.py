@@ -24,7 +24,12 @@ from tests import report, util
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="reference sources not present")]
 DEV = "cuda:0"
 SR, P, NU = 44100, 512, 768
-GATE_RMS = 2e-6
+# The reference runs its DSP with CUDA operators here, the kernels follow the reference's CPU path (the oracle, SURVEY
+# A.10): torch's fp32 cumsum accumulates in fp32 on CUDA and in fp64 on the CPU (all-pass phase, SuperFast / SineGen frame
+# scans), so reference-on-GPU differs from reference-on-CPU by a few 1e-6 absolute at this signal level (RMS 0.06-0.08,
+# i.e. <= 1e-4 relative; measured: Sins 5.8e-6, CombSub 6.3e-6, CombSubFast 9e-7, CombSubSuperFast 2.2e-5).  The bound is
+# the north star's 1e-4 RMS; parity at the 1e-8 level is pinned on identical controls by the golden tests.
+GATE_RMS = 1e-4
 
 
 @contextlib.contextmanager
@@ -52,10 +57,7 @@ CASES = {
                     make=lambda V: V.CombSub(SR, P, 256, 512, 256, n_unit=NU, n_spk=2), uniform=True, parts=True),
     "CombSubSuperFast": dict(model={"type": "CombSubSuperFast", "win_length": 2048, "n_spk": 2},
                              make=lambda V: V.CombSubSuperFast(SR, P, 2048, n_unit=NU, n_spk=2), uniform=False, parts=False,
-                             # fast_source_gen's frame cumsum runs in fp32 on CUDA (fp64-accumulated on the CPU, which is the
-                             # oracle the kernel follows): reference-on-GPU vs reference-on-CPU differ at the
-                             # 1e-5-cycle level, amplified by sr/f0 in the sinc argument -> the official bound applies here
-                             tol=1e-4),
+                             ),
     "CombSubFast": dict(model={"type": "CombSubFast", "n_spk": 2},
                         make=lambda V: V.CombSubFast(SR, P, n_unit=NU, n_spk=2), uniform=True, parts=False),
 }

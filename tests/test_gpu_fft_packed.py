@@ -19,7 +19,7 @@ SR, P = G.SR, G.P
 @pytest.fixture(autouse=True)
 def _restore():
     yield
-    ops.set_fft_arith("scalar")
+    ops.set_fft_arith("packed")          # the library default
 
 
 def _model(kind, B, nF):
@@ -44,6 +44,7 @@ def test_packed_matches_scalar(kind):
     f0 = syn.make_f0(B, nF, SR, P, seed=4, unvoiced_fraction=0.2).to(DEV)
     noise = (syn.normal_noise((B, nF * P), 5) if kind == "superfast" else syn.uniform_noise(B, nF * P, 5)).to(DEV)
     with torch.no_grad():
+        ops.set_fft_arith("scalar")
         ref = model(None, f0, None, noise=noise)[0]
         ops.set_fft_arith("packed")
         got = model(None, f0, None, noise=noise)[0]
