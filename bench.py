@@ -537,6 +537,8 @@ def main():
                     help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
     ap.add_argument("--fft-arith", default="packed", choices=["scalar", "packed"],
                     help="A/B switch: packed f32x2 complex additions in the FFT kernels (ops.set_fft_arith)")
+    ap.add_argument("--sins-impl", default="auto", choices=["auto", "split", "fused"],
+                    help="A/B switch (ops.set_sins_impl): bank fused into the FFT-domain FIR kernel, or separate kernels")
     ap.add_argument("--overlap", type=int, default=None,
                     help="A/B switch (ops.set_overlap): 0 in order, 1 impulse responses beside the bank, k >= 2 "
                          "additionally k staggered sub-batches on two streams")
@@ -573,6 +575,8 @@ def main():
         run.ops.set_fir_impl(args.fir_impl)
     if args.overlap is not None:
         run.ops.set_overlap(args.overlap)
+    if args.sins_impl != "auto":
+        run.ops.set_sins_impl(args.sins_impl)
     if args.fft_arith != "packed":
         run.ops.set_fft_arith(args.fft_arith)
     B, nF, T = run.B, run.nF, run.T

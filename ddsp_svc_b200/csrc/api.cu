@@ -25,6 +25,13 @@ int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, cons
                    int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,
                    int nF, int P, cudaStream_t st);
 
+bool fir_fft_selected();
+bool sins_fused_supported(int P, int taps_allpass, int taps_noise, int H);
+int sins_fused_launch(const float* f0, const double* frame_phase, const float* c_amp, int64_t ctrl_stride, int H,
+                      double sampling_rate, int round_fp32, const float* ir_allpass, int taps_allpass, float* harmonic,
+                      const float* noise_in, const float* ir_noise, int taps_noise, float* noise_out, float* signal,
+                      uint64_t seed, int64_t utt_off, int B, int nF, int P, cudaStream_t st);
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace b2d
@@ -100,6 +107,18 @@ static SideLane* side_lane() {
     return &l;
 }
 }  // namespace b2d
+
+// 0 = auto = 1 (separate bank kernel, measured faster), 1 = separate bank kernel, 2 = bank fused into the FFT-domain FIR
+// kernel.  Measured on B200 (B = 32 x 10 s): fused 0.800 ms/step, separate 0.789: with 168 registers only three 4-warp CTAs
+// fit an SM, and ONE warp per scheduler in the bank phase cannot keep the FMA pipe busy (the stand-alone bank kernel has
+// four), so the fused kernel takes bank + FIR = 0.64 ms -- the expected filling of the FIR's idle issue slots does not
+// happen.  It stays selectable: one launch less, no [B, T] sinusoid round trip.
+namespace b2d { std::atomic<int> g_sins_impl{0}; }
+extern "C" int b2d_set_sins_impl(int impl) {
+    if (impl < 0 || impl > 2) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_sins_impl: %d not in {0, 1, 2}", impl);
+    b2d::g_sins_impl.store(impl, std::memory_order_relaxed);
+    return 0;
+}
 
 extern "C" int b2d_set_overlap(int mode) {
     if (mode < -64 || mode > 64) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_overlap: %d outside [-64, 64]", mode);
@@ -185,6 +204,33 @@ extern "C" int b2d_sins_synth(const float* f0_frames, const double* frame_phase,
         return b2d_ir_build(c_noise, ctrl_stride, B2D_IR_MAG_HANN, nullptr, dft_tables_noise, B, n_frames, n_mag_noise,
                             sampling_rate, ir_n, q2);
     };
+    // ---- fused path: impulse responses (side by side on the two side streams), then ONE kernel: bank + both FIRs + mix ----
+    const int simpl = b2d::g_sins_impl.load(std::memory_order_relaxed);
+    const bool can_fuse = b2d::sins_fused_supported(block, La, Ln, n_harmonics) && b2d::fir_fft_selected();
+    if (simpl == 2 && !can_fuse)
+        return b2d::fail(B2D_ERR_UNSUPPORTED, "sins_synth: fused kernel needs block 512, <= 512 taps, <= 128 harmonics and the FFT-domain FIR");
+    if (can_fuse && simpl == 2) {
+        cudaError_t fe = cudaSuccess;
+        int rc;
+        if (lane) {
+            fe = cudaEventRecord(lane->fork, st);
+            if (fe == cudaSuccess) fe = cudaStreamWaitEvent(lane->hi, lane->fork, 0);
+            if (fe == cudaSuccess) fe = cudaStreamWaitEvent(lane->lo, lane->fork, 0);
+            if (fe != cudaSuccess) return b2d::fail((int)fe, "sins_synth: fork: %s", cudaGetErrorString(fe));
+            rc = irs(lane->hi, lane->lo);
+            fe = cudaEventRecord(lane->join, lane->hi);
+            if (fe == cudaSuccess) fe = cudaStreamWaitEvent(st, lane->join, 0);
+            if (fe == cudaSuccess) fe = cudaEventRecord(lane->join2, lane->lo);
+            if (fe == cudaSuccess) fe = cudaStreamWaitEvent(st, lane->join2, 0);
+        } else {
+            rc = irs(st, st);
+        }
+        if (rc) return rc;
+        if (fe != cudaSuccess) return b2d::fail((int)fe, "sins_synth: join: %s", cudaGetErrorString(fe));
+        return b2d::sins_fused_launch(f0_frames, frame_phase, c_amp, ctrl_stride, n_harmonics, sampling_rate, round_fp32,
+                                      ir_ap, La, harmonic, noise_in, ir_n, Ln, noise_out, signal, seed, utterance_offset,
+                                      B, n_frames, block, st);
+    }
     if (!lane) {                                       // in order on the caller's stream
         int rc = irs(st, st);
         if (!rc) rc = bank(0, B, st);

@@ -511,6 +511,12 @@ static int fir_auto_impl() {
     return v;
 }
 
+// true when the FFT-domain kernel is what ltv_fir_launch would pick (the Sins driver then may use its fused variant)
+bool fir_fft_selected() {
+    const int sel = g_fir_impl.load(std::memory_order_relaxed);
+    return (sel == 0 ? fir_auto_impl() : sel) == 4;
+}
+
 // internal entry (also used by the CombSub driver): mix = y1 (+ y2) (+ addend)
 int ltv_fir_launch(const float* x1, const float* ir1, int taps1, float* y1, const float* x2, const float* ir2,
                    int taps2, float* y2, const float* addend, float* mix, uint64_t seed, int64_t utt_off, int B,

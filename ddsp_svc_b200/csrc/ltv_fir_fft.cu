@@ -27,6 +27,7 @@
 // the host emulation in tests/emu/ (tests/test_emu_ltv_fir_fft.py, race check in tests/test_emu_tsan.py).
 #ifndef B2D_HOST_EMU
 #include "b2d_common.cuh"
+#include "sins_bank_math.cuh"
 #endif
 #include "fft_smem.cuh"
 
@@ -44,6 +45,23 @@ struct FftFirJob {
     int L;
 };
 
+// BANK variant (Sins): job 0's input is not read from memory but synthesised in the kernel -- the additive sinusoid bank
+// of the hop (sins_bank_math.cuh, the arithmetic of sins_bank.cu) is evaluated straight into the FFT buffer.  The FIR
+// kernel alone is latency bound (barriers, shared-memory round trips: ~54 % issue slots used, FMA pipe 37 %) and the bank
+// alone is FMA / SFU bound; in one kernel the warps of the three resident CTAs sit in different phases, so the bank's
+// arithmetic fills the issue slots the transforms leave empty, the [B, T] sinusoid tensor never exists (113 MB of HBM
+// traffic) and a launch disappears.
+struct FftFirBank {
+    const float* f0;             // [B, nF]
+    const double* frame_phase;   // [B, nF] unwrapped cycles at frame starts (phase_scan.cu)
+    const float* c_amp;          // raw amplitudes, frame stride ctrl_stride
+    long long ctrl_stride;
+    int H;
+    double inv_sr;
+    float nyquist;
+    int round_fp32;
+};
+
 struct FftFirParams {
     FftFirJob job[2];
     const float* addend;
@@ -51,11 +69,13 @@ struct FftFirParams {
     unsigned long long seed;
     long long utt_off;
     int nF, G;
+    FftFirBank bank;
 };
 
-template <int N, int NJ> constexpr size_t fir_fft_smem() {
+constexpr int kBankRow = 128;            // harmonics per activated amplitude row of the BANK variant (H <= 128)
+template <int N, int NJ, int NBANK = 0> constexpr size_t fir_fft_smem() {
     return (size_t)3 * NJ * Plan<N>::kPad * sizeof(float2) + (size_t)(Plan<N>::kTw2 + Plan<N>::kTw3) * sizeof(float2) +
-           (size_t)NJ * kRing * sizeof(float);
+           (size_t)NJ * kRing * sizeof(float) + (NBANK ? (size_t)5 * kBankRow * sizeof(float) : 0);
 }   // N = 1024: NJ = 2 -> 70528 B (3 CTAs per SM), NJ = 1 -> 36224 B;  N = 2048: NJ = 1 -> 64384 B, NJ = 2 -> 124800 B
 
 // spectra of two real sequences a, c from Z = FFT(a + j c):  A[k] = (Z[k] + conj Z[N-k]) / 2,  C[k] = (Z[k] - conj Z[N-k]) / 2j
@@ -65,7 +85,8 @@ __device__ __forceinline__ void split2(float2 zk, float2 zm, float2& A, float2& 
 }
 
 // PK: complex additions as packed f32x2 instructions (fft_regs.cuh Ar<true>): same results, fewer issue slots
-template <int N, int NJ, bool PK>
+// NBANK: 0 = inputs from memory / Philox; 4 or 8 = job 0 is the sinusoid bank with that many bases of 16 harmonics
+template <int N, int NJ, bool PK, int NBANK = 0>
 __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_fir_fft_kernel(FftFirParams p) {
     constexpr int kN = N, kPad = Plan<N>::kPad, kTw2 = Plan<N>::kTw2, kTw3 = Plan<N>::kTw3;
     constexpr int kBins = N / 2 / kThreads;          // bins k = tid + 128 u per thread (DC.. N/2-1); Nyquist on thread 0
@@ -76,6 +97,8 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
     float2* tw2 = F + 3 * NJ * kPad;
     float2* tw3 = tw2 + kTw2;
     float* ring = reinterpret_cast<float*>(tw3 + kTw3);          // [NJ][kRing]
+    float* bank_act = ring + NJ * kRing;                         // BANK: [3][128] activated amplitudes of frames g, g+1, g+2
+    float* bank_dlt = bank_act + 3 * kBankRow;                   //       [2][128] their differences
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
@@ -121,6 +144,34 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
 #pragma unroll
             for (int e = 0; e < 4; ++e) buf[padi(z + i0 + e)] = make_float2(0.f, 0.f);
     };
+
+#ifndef B2D_HOST_EMU
+    // BANK: the 4 samples i0..i0+3 of hop g of the sinusoid bank (amplitude rows r, r+1 of bank_act) -> (x, phi x)
+    auto bank_x = [&](int g, int r, bool present, float2* buf) {
+        const int i0 = tid << 2;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (NBANK && present) {
+            const float* f0row = p.bank.f0 + (size_t)b * nF;
+            const double fk = (double)__ldg(f0row + g), dk = (double)__ldg(f0row + min(g + 1, nF - 1)) - fk;
+            const double S = __ldg(p.bank.frame_phase + (size_t)b * nF + g);
+            float x32[4], phase[4], frac[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                x32[s] = b2d_bank::sample_phase(S, fk, dk, i0 + s, 0.5 / (double)kHop, p.bank.inv_sr, p.bank.round_fp32);
+                phase[s] = x32[s] * B2D_TWO_PI_F;
+                frac[s] = (float)(i0 + s) * (1.0f / kHop);
+            }
+            b2d_bank::bank_group<(NBANK ? NBANK : 1), true>(bank_act + r * kBankRow, bank_dlt + r * kBankRow, 0, x32, phase, frac, acc);
+        }
+        const float s = 1.0f / kHop;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) buf[padi(i0 + e)] = make_float2(acc[e], acc[e] * ((float)(i0 + e) * s));
+#pragma unroll
+        for (int z = kHop; z < kN / 2; z += kHop)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) buf[padi(z + i0 + e)] = make_float2(0.f, 0.f);
+    };
+#endif
 
     // spectrum of frame g per job: bins k = tid + 128 u; thread 0 additionally holds DC (u = 0) and Nyquist (real)
     float2 Hp[NJ][kBins];
@@ -177,10 +228,37 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
     for (int g = gs; g <= ge; g += 2) {
         const bool has_a = g >= 0, has_b = g + 1 <= nF - 1;      // properties of the utterance only, not of the chunking
         // ---- forward: both hops of every job and the impulse-response pairs as one batch ----
+#ifndef B2D_HOST_EMU
+        if (NBANK) {
+            // activated amplitudes of frames g, g+1, g+2 (clamped: A[nF] := A[nF-1], ddsp/core.py:68) and their differences.
+            // The rows were last read before the previous iteration's transform barriers.
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int k = min(max(g + r, 0), nF - 1);
+                float v = 0.f;
+                if (tid < p.bank.H)
+                    v = b2d_bank::activate_amp(__ldg(p.bank.c_amp + ((size_t)b * nF + k) * p.bank.ctrl_stride + tid),
+                                               __ldg(p.bank.f0 + (size_t)b * nF + k), tid, p.bank.nyquist);
+                bank_act[r * kBankRow + b2d_bank::slot_of(tid)] = v;
+            }
+            __syncthreads();
+            bank_dlt[tid] = bank_act[kBankRow + tid] - bank_act[tid];
+            bank_dlt[kBankRow + tid] = bank_act[2 * kBankRow + tid] - bank_act[kBankRow + tid];
+            __syncthreads();
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            load_x(j, g, has_a, F + j * kPad);
-            load_x(j, g + 1, has_b, F + (NJ + j) * kPad);
+#ifndef B2D_HOST_EMU
+            if (NBANK && j == 0) {
+                bank_x(g, 0, has_a, F + j * kPad);
+                bank_x(g + 1, 1, has_b, F + (NJ + j) * kPad);
+            } else
+#endif
+            {
+                load_x(j, g, has_a, F + j * kPad);
+                load_x(j, g + 1, has_b, F + (NJ + j) * kPad);
+            }
             load_ir_pair(j, g + 1, g + 2, true);
         }
         __syncthreads();
@@ -267,16 +345,16 @@ bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs) {
     return P == kHop && taps1 > 0 && (njobs == 1 || taps2 > 0) && tmax <= 1024;
 }
 
-template <int N, int NJ, bool PK>
+template <int N, int NJ, bool PK, int NBANK = 0>
 static int launch_fir_fft_as(const FftFirParams& p, dim3 grid, cudaStream_t st) {
-    constexpr size_t smem = fir_fft_smem<N, NJ>();
+    constexpr size_t smem = fir_fft_smem<N, NJ, NBANK>();
     // per launch, like the direct-form kernels: function attributes are per device and this costs ~1 us
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK, NBANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
     }
-    cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    ltv_fir_fft_kernel<N, NJ, PK><<<grid, kThreads, smem, st>>>(p);
+    cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK, NBANK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    ltv_fir_fft_kernel<N, NJ, PK, NBANK><<<grid, kThreads, smem, st>>>(p);
     return check_launch("ltv_fir(fft)");
 }
 
@@ -291,7 +369,7 @@ int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, 
     const int njobs = ir2 ? 2 : 1;
     if (!ltv_fir_fft_supported(P, taps1, taps2, njobs))
         return fail(B2D_ERR_UNSUPPORTED, "ltv_fir(fft): needs block size %d and at most 1024 taps", kHop);
-    FftFirParams p;
+    FftFirParams p = {};
     p.job[0] = {x1, ir1, y1, taps1};
     p.job[1] = {x2, ir2, y2, njobs == 2 ? taps2 : taps1};
     p.addend = addend; p.mix = mix; p.seed = seed; p.utt_off = utt_off; p.nF = nF;
@@ -306,6 +384,39 @@ int ltv_fir_fft_launch(const float* x1, const float* ir1, int taps1, float* y1, 
     const int tmax = njobs == 2 ? (taps1 > taps2 ? taps1 : taps2) : taps1;
     if (tmax <= kHop) return njobs == 2 ? launch_fir_fft<1024, 2>(p, grid, st) : launch_fir_fft<1024, 1>(p, grid, st);
     return njobs == 2 ? launch_fir_fft<2048, 2>(p, grid, st) : launch_fir_fft<2048, 1>(p, grid, st);
+}
+
+// Sins fused: harmonic = allpass(bank(f0, amplitudes)), noise = filter(white noise), signal = harmonic + noise in ONE
+// kernel (block size 512, two filters of at most 512 taps, at most 128 harmonics).
+bool sins_fused_supported(int P, int taps_allpass, int taps_noise, int H) {
+    return P == kHop && taps_allpass > 0 && taps_noise > 0 && taps_allpass <= kHop && taps_noise <= kHop &&
+           !(taps_allpass & 1) && !(taps_noise & 1) && H > 0 && H <= kBankRow;
+}
+
+int sins_fused_launch(const float* f0, const double* frame_phase, const float* c_amp, int64_t ctrl_stride, int H,
+                      double sampling_rate, int round_fp32, const float* ir_allpass, int taps_allpass, float* harmonic,
+                      const float* noise_in, const float* ir_noise, int taps_noise, float* noise_out, float* signal,
+                      uint64_t seed, int64_t utt_off, int B, int nF, int P, cudaStream_t st) {
+    if (!sins_fused_supported(P, taps_allpass, taps_noise, H))
+        return fail(B2D_ERR_UNSUPPORTED, "sins(fused): needs block size %d, <= %d taps, <= %d harmonics", kHop, kHop, kBankRow);
+    const float* ptrs[] = {noise_in, harmonic, noise_out, signal};
+    for (const float* q : ptrs)
+        if (q && !aligned16(q)) return fail(B2D_ERR_ALIGN, "sins(fused): signal pointers must be 16-byte aligned");
+    if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "sins(fused): batch %d > 65535", B);
+    FftFirParams p;
+    p.job[0] = {nullptr, ir_allpass, harmonic, taps_allpass};
+    p.job[1] = {noise_in, ir_noise, noise_out, taps_noise};
+    p.addend = nullptr; p.mix = signal; p.seed = seed; p.utt_off = utt_off; p.nF = nF;
+    p.bank.f0 = f0; p.bank.frame_phase = frame_phase; p.bank.c_amp = c_amp; p.bank.ctrl_stride = ctrl_stride;
+    p.bank.H = H; p.bank.inv_sr = 1.0 / sampling_rate; p.bank.nyquist = (float)(sampling_rate / 2.0);
+    p.bank.round_fp32 = round_fp32;
+    int G = 32;
+    while (G > 2 && (long long)B * ((nF + G - 1) / G) < 148LL * 2) G >>= 1;
+    p.G = G;
+    const dim3 grid((unsigned)((nF + p.G - 1) / p.G), B);
+    const bool pk = g_fft_packed.load(std::memory_order_relaxed) != 0;
+    if (H <= 64) return pk ? launch_fir_fft_as<1024, 2, true, 4>(p, grid, st) : launch_fir_fft_as<1024, 2, false, 4>(p, grid, st);
+    return pk ? launch_fir_fft_as<1024, 2, true, 8>(p, grid, st) : launch_fir_fft_as<1024, 2, false, 8>(p, grid, st);
 }
 
 }  // namespace b2d

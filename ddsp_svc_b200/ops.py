@@ -16,13 +16,17 @@ IR_ALLPASS, IR_MAG_HANN, IR_MAG_DYNAMIC = 0, 1, 2
 _launches = 0
 _tables = {}
 _overlap_mode = 1   # mirrors the library's default (b2d_set_overlap)
+_sins_impl = "auto"
+_fir_impl = "auto"
 _tables_lock = threading.Lock()
 
 
 def set_fir_impl(impl):
     """'auto' (FFT-domain kernel for block size 512 and <= 1024 taps, else CUDA cores), 'cuda' (CUDA-core direct
     form), 'tc' (tcgen05 3xTF32 kernel, block size 512), 'cuda8' (older scalar CUDA-core kernel) or 'fft'."""
+    global _fir_impl
     _lib.check(_lib.lib().b2d_set_fir_impl({"auto": 0, "cuda": 1, "tc": 2, "cuda8": 3, "fft": 4}[impl]), "b2d_set_fir_impl")
+    _fir_impl = impl
 
 
 def set_ir_impl(impl):
@@ -227,8 +231,9 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
                           int(block), H, Ma, Mn, float(sampling_rate), 0 if infer else 1, signal.data_ptr(),
                           _ptr(harmonic), _ptr(noise), ws.data_ptr(), ws_bytes, _stream())
     _lib.check(rc, "b2d_sins_synth")
+    fused = _sins_impl == "fused" and Ma == Mn and int(block) == 512 and Ma <= 257 and H <= 128 and _fir_impl in ("auto", "fft")
     nsplit = max(1, min(abs(_overlap_mode), B)) if abs(_overlap_mode) >= 2 else 1
-    _count(2 + nsplit * (2 if Ma == Mn else 3))
+    _count(3 if fused else 2 + nsplit * (2 if Ma == Mn else 3))
     return signal, harmonic, noise
 
 
@@ -422,3 +427,10 @@ def set_overlap(mode):
     global _overlap_mode
     _lib.check(_lib.lib().b2d_set_overlap(int(mode)), "b2d_set_overlap")
     _overlap_mode = int(mode)
+
+
+def set_sins_impl(name):
+    """'auto' (= 'split': separate bank kernel, measured faster) | 'split' | 'fused' (bank inside the FFT-domain FIR kernel)."""
+    global _sins_impl
+    _lib.check(_lib.lib().b2d_set_sins_impl({"auto": 0, "split": 1, "fused": 2}[name]), "b2d_set_sins_impl")
+    _sins_impl = name

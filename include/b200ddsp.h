@@ -242,6 +242,13 @@ int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude,
  * (atomic, read once per call). */
 int b2d_set_fft_arith(int packed);
 
+/* b2d_sins_synth: 0 (default) = 1 = separate oscillator-bank kernel next to the impulse-response builds, then the FIR
+ * kernel; 2 = the bank is evaluated inside the FFT-domain FIR kernel (block 512, both filters <= 512 taps, <= 128
+ * harmonics, FIR selection 0/4, else an error): one kernel computes bank, both FIRs and the mix and the [B, T] sinusoid
+ * tensor is never materialised -- measured 1.4 % slower on B200 (see api.cu), kept as a tested alternative.  Same results
+ * (identical bank arithmetic).  Process-wide test/diagnostic knob (atomic, read once per call). */
+int b2d_set_sins_impl(int impl);
+
 /* How b2d_sins_synth overlaps its independent kernels on an internal side stream that is joined on the caller's stream
  * before the call returns (event record/wait only; legal under stream capture).  0: every kernel on the caller's
  * stream, in order.  1: impulse-response builds next to the oscillator bank.  k >= 2: additionally the batch is cut into

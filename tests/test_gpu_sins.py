@@ -207,3 +207,33 @@ def test_full_size_properties():
     assert e_tg < 2e-6
     assert lin.abs().max().item() < 5e-5   # inputs of amplitude ~2: fp32 rounding of a 510-term sum
     assert e_row < GATE_RMS
+
+
+@pytest.mark.parametrize("H", [128, 64, 31, 1])
+def test_fused_bank_fir_kernel_equals_split_kernels(H):
+    """`fused` evaluates the oscillator bank inside the FFT-domain FIR kernel; `split` (the default) runs the stand-alone
+    bank kernel + FIR kernel.  Same bank arithmetic, same transforms: the three outputs must agree to round-off (the two
+    compilations may contract differently), for full and partial harmonic groups, in-kernel and explicit noise."""
+    B, nF = 3, 70
+    sm = syn.sins_split_map(H, 256, 256)
+    f0 = syn.make_f0(B, nF, SR, P, seed=21, unvoiced_fraction=0.1, sweep_row=1).to(DEV)
+    dense = syn.make_ctrl(B, nF, sm, seed=22)[0].to(DEV)
+    dc = syn.split_views(dense, sm)
+    noise = syn.uniform_noise(B, nF * P, 23).to(DEV)
+    fp, _ = ops.phase_scan(f0, P, SR)
+    outs = {}
+    try:
+        for impl in ("split", "fused"):
+            ops.set_sins_impl(impl)
+            outs[impl] = [ops.sins_synth(f0, fp, dc["amplitudes"], dc["group_delay"], dc["noise_magnitude"], P, SR,
+                                         noise_in=noise),
+                          ops.sins_synth(f0, fp, dc["amplitudes"], dc["group_delay"], dc["noise_magnitude"], P, SR,
+                                         seed=5, utterance_offset=7)]
+    finally:
+        ops.set_sins_impl("auto")
+    worst = 0.0
+    for a, b in zip(outs["split"], outs["fused"]):
+        for x, y in zip(a, b):
+            worst = max(worst, (x - y).abs().max().item())
+    report.record("sins_fused_vs_split/H%d" % H, max_diff=worst, identical=worst == 0.0)
+    assert worst < 1e-7
