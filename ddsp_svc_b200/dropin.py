@@ -80,6 +80,9 @@ def patch_reference():
     saved = {name: getattr(ref_vocoder, name) for name in names}
     for name in names:
         setattr(ref_vocoder, name, getattr(vocoder, name))
+    from . import frontend                      # Volume_Extractor (numpy in -> numpy out like the reference, computed on the GPU)
+    saved["Volume_Extractor"] = ref_vocoder.Volume_Extractor
+    ref_vocoder.Volume_Extractor = frontend.Volume_Extractor
     try:
         import nsf_hifigan.models as ref_nsf
     except ImportError as e:                    # enhancer stack not importable: synthesizers only (reported below)
@@ -94,7 +97,7 @@ def patch_reference():
 
 def unpatch_reference(saved):
     import ddsp.vocoder as ref_vocoder
-    for name in ("Sins", "CombSub", "CombSubSuperFast", "CombSubFast"):
+    for name in ("Sins", "CombSub", "CombSubSuperFast", "CombSubFast", "Volume_Extractor"):
         if name in saved:
             setattr(ref_vocoder, name, saved[name])
     if "SineGen" in saved:

@@ -242,6 +242,23 @@ int b2d_combsubfast_filter(const float* comb, const float* c_harmonic_magnitude,
  * (atomic, read once per call). */
 int b2d_set_fft_arith(int packed);
 
+/* ---- caller-side prologue / epilogue -------------------------------------------------------------
+ * Volume_Extractor.extract (ddsp/vocoder.py:147-157): audio [B, n_samples] -> volume [B, n_samples / hop + 1],
+ * volume[n] = sqrt(mean(pad_reflect(audio^2, hop/2, (hop+1)/2)[n hop : (n+1) hop])). */
+int b2d_volume_extract(const float* audio, int B, int n_samples, int hop, float* volume, void* stream);
+
+/* Silence mask at frame rate (main.py:211-213): mask[n] = max over frames n-4..n+4 (clamped) of (volume > threshold). */
+int b2d_volume_mask(const float* volume, int B, int n_frames, float threshold, float* mask_frames, void* stream);
+
+/* `seg_output *= upsample(mask, block)[frame_offset*block : (frame_offset+n_frames)*block]` in place (main.py:215,260;
+ * upsample = ddsp/core.py:66-70: linear, last frame held).  signal [B, n_frames*block], mask_frames [B, n_mask_frames]. */
+int b2d_mask_apply(float* signal, const float* mask_frames, int B, int n_mask_frames, int frame_offset, int n_frames,
+                   int block, void* stream);
+
+/* Segment cross-fade (main.py:142-149): out[0 : idx + len_b] = a[:idx] | (1-k) a[idx:] + k b[:len_a-idx] | b[len_a-idx:],
+ * k = linspace(0, 1, len_a - idx) evaluated in fp64.  Requires 0 <= idx < len_a and len_a - idx <= len_b. */
+int b2d_cross_fade(const float* a, int64_t len_a, const float* b, int64_t len_b, int64_t idx, float* out, void* stream);
+
 /* b2d_sins_synth: 0 (default) = 1 = separate oscillator-bank kernel next to the impulse-response builds, then the FIR
  * kernel; 2 = the bank is evaluated inside the FFT-domain FIR kernel (block 512, both filters <= 512 taps, <= 128
  * harmonics, FIR selection 0/4, else an error): one kernel computes bank, both FIRs and the mix and the [B, T] sinusoid
