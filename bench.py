@@ -24,7 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SR, P = 44100, 512
-OTHER_WORKLOADS = ("sins_cfg1", "combsub", "superfast", "combsubfast", "sinegen", "srcmod")
+OTHER_WORKLOADS = ("sins_cfg1", "combsub", "superfast", "combsubfast", "sinegen", "srcmod", "mel", "maskmul")
 
 # N -> (gather mode, chunks, compute streams) chosen by `--gather auto` (measured on B200)
 # round 2, ms/step at N=8 with 0.84 ms of kernels (profiles/r2_scale_m8_*.json): peer stores 1.077 | per-chunk peer stores
@@ -48,6 +48,10 @@ WORKLOADS = {
                     label="nsf_hifigan SineGen, B=64 x 10 s, 9 harmonics (BASELINE configs[4])"),
     "srcmod": dict(kind="srcmod", B=64, sec=10, dim=9,
                    label="nsf_hifigan SourceModuleHnNSF = SineGen + tanh(Linear(9->1)) fused, B=64 x 10 s (SURVEY 8f)"),
+    "mel": dict(kind="mel", B=32, sec=10, n_mels=128,
+                label="nsf_hifigan STFT.get_mel log-mel front end, B=32 x 10 s, n_fft 2048 / hop 512 / 128 mels (SURVEY 8f)"),
+    "maskmul": dict(kind="maskmul", B=32, sec=10,
+                    label="caller epilogue `seg_output *= upsample(mask, block)` (main.py:215,260), B=32 x 10 s (SURVEY 8f)"),
 }
 
 
@@ -69,6 +73,10 @@ def algorithmic_bytes(w, nF):
         return 4 * B * nF + 4 * B * T * w["dim"]
     if w["kind"] == "srcmod":
         return 4 * B * nF + 4 * B * T
+    if w["kind"] == "mel":
+        return 4 * B * T + 4 * B * nF * w["n_mels"]
+    if w["kind"] == "maskmul":
+        return 4 * B * nF + 2 * 4 * B * T
     raise ValueError(w["kind"])
 
 
@@ -98,11 +106,36 @@ def oracle_forward(w, f0, ctrls):
         return tp.superfast_forward(f0, ctrls, SR, P, w["win"])
     if k == "combsubfast":
         return tp.combsubfast_forward(f0, ctrls, SR, P)
+    if k == "mel":
+        from oracle import mel as om
+        return {"out": om.get_mel(f0)}             # `f0` carries the audio for this kind
+    if k == "maskmul":
+        from oracle import frontend as fe
+        import torch
+        return {"out": torch.cat([fe.mask_apply(f0[i:i + 1], ctrls[0].numpy(), P) for i in range(f0.shape[0])])}
     if k == "srcmod":
         import torch
         g = torch.Generator().manual_seed(5)
         return tp.source_module_forward(f0[..., 0], P, SR, torch.randn(1, w["dim"], generator=g) / 3, torch.zeros(1), w["dim"] - 1)
     return tp.sinegen_forward(f0[..., 0], P, SR, w["dim"] - 1)
+
+
+def oracle_inputs(w, batch, nF):
+    """seeded CPU inputs of the oracle for `batch` utterances: (f0 or waveform, controls or mask)"""
+    import torch
+    from ddsp_svc_b200 import synthetic as syn
+    if w["kind"] in ("mel", "maskmul"):
+        g = torch.Generator().manual_seed(99)
+        audio = 0.1 * torch.randn(batch, nF * P, generator=g)
+        return audio, ([(torch.rand(nF, generator=g) > 0.2).float()] if w["kind"] == "maskmul" else None)
+    sm = split_map_of(w)
+    return syn.make_f0(batch, nF, SR, P), (syn.make_ctrl(batch, nF, sm)[1] if sm else None)
+
+
+def _first(ctrls, n):
+    if ctrls is None:
+        return None
+    return {k: v[:n] for k, v in ctrls.items()} if isinstance(ctrls, dict) else ctrls
 
 
 # ------------------------------------------------------------------------------------------
@@ -181,12 +214,10 @@ def cpu_reference_run(w, batch, reps, threads=None):
     cores = threads or best_thread_count(w)
     torch.set_num_threads(cores)
     nF = syn.n_frames_for(w["sec"], SR, P)
-    sm = split_map_of(w)
-    f0 = syn.make_f0(batch, nF, SR, P)
-    ctrls = syn.make_ctrl(batch, nF, sm)[1] if sm else None
+    f0, ctrls = oracle_inputs(w, batch, nF)
     best = None
     with torch.no_grad():
-        oracle_forward(w, f0[:1], {k: v[:1] for k, v in ctrls.items()} if ctrls else None)  # warm-up (small)
+        oracle_forward(w, f0[:1], _first(ctrls, 1))  # warm-up (small)
         for _ in range(reps):
             t0 = time.perf_counter()
             oracle_forward(w, f0, ctrls)
@@ -210,9 +241,7 @@ def best_thread_count(w):
         return _best_threads[key]
     ncpu = os.cpu_count() or 1
     nF = syn.n_frames_for(min(w["sec"], 2), SR, P)
-    sm = split_map_of(w)
-    f0 = syn.make_f0(2, nF, SR, P)
-    ctrls = syn.make_ctrl(2, nF, sm)[1] if sm else None
+    f0, ctrls = oracle_inputs(w, 2, nF)
     best, best_t = ncpu, None
     for n in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
         torch.set_num_threads(n)
@@ -273,6 +302,21 @@ class Runner:
         nF = self.nF = syn.n_frames_for(w["sec"], SR, P)
         self.T = nF * P
         self.sm = split_map_of(w)
+        if w["kind"] in ("mel", "maskmul"):            # waveform-in workloads on either side of the synthesizer
+            from ddsp_svc_b200 import frontend, mel
+            g = torch.Generator().manual_seed(99 + rank)
+            self.audio_h = (0.1 * torch.randn(B, self.T, generator=g)).pin_memory()
+            self.audio_d = self.audio_h.to(dev)
+            self.h2d = self.audio_h.numel() * 4
+            self.sg, self.width = False, 1
+            if w["kind"] == "mel":
+                self.stft = mel.STFT(SR, w["n_mels"], 2048, 2048, P, 40, 16000)
+                self.out_h = torch.empty(B, w["n_mels"], nF, dtype=torch.float32).pin_memory()
+            else:
+                self.frontend = frontend
+                self.mask_d = (torch.rand(B, nF, generator=g) > 0.2).float().to(dev)
+                self.out_h = torch.empty(B, self.T, dtype=torch.float32).pin_memory()
+            return
         self.f0_h = syn.make_f0(B, nF, SR, P, seed=1234 + rank).pin_memory()
         self.f0_d = self.f0_h.to(dev)
         self.h2d = self.f0_h.numel() * 4
@@ -303,7 +347,14 @@ class Runner:
         self.out_h = torch.empty(B, self.T, dtype=torch.float32).pin_memory()
 
     # one pass of the hot path with inputs resident in HBM; returns the waveform to gather
+    def _wave_op(self, audio, lo=0):
+        if self.w["kind"] == "mel":
+            return self.stft.get_mel(audio)
+        return self.frontend.mask_apply_(audio, self.mask_d[lo:lo + audio.shape[0]], P)
+
     def step(self, f0=None):
+        if self.w["kind"] in ("mel", "maskmul"):
+            return self._wave_op(self.audio_d)
         f0 = self.f0_d if f0 is None else f0
         if self.sg:
             return self.model(f0[..., 0], P, rand_ini=self.rand_ini, utterance_offset=self.rank * self.B)
@@ -336,6 +387,8 @@ class Runner:
         from ddsp_svc_b200 import HostPipeline
         if getattr(self, "_pipe", None) is None or self._pipe.chunks != chunks:
             self._pipe = HostPipeline(self.dev, chunks=chunks, compute_streams=self.e2e_streams)
+        if self.w["kind"] in ("mel", "maskmul"):
+            return self._pipe.run({"audio": self.audio_h}, lambda d, lo, hi: self._wave_op(d["audio"], lo), self.out_h)
         host = {"f0": self.f0_h}
         if not self.sg:
             host["dense"] = self.dense_h
@@ -353,11 +406,13 @@ class Runner:
 
     def kernels(self):
         """name -> callable launching exactly that kernel (inputs prepared beforehand)."""
+        k = self.w["kind"]
+        if k in ("mel", "maskmul"):
+            return {("mel_kernel" if k == "mel" else "mask_apply_kernel"): lambda: self._wave_op(self.audio_d)}
         ops, w, c, f0, B, nF, T = self.ops, self.w, getattr(self, "ctrl_d", None), self.f0_d, self.B, self.nF, self.T
         torch, dev = self.torch, self.dev
         L = ops._lib.lib()
         st = torch.cuda.current_stream().cuda_stream
-        k = w["kind"]
         if k == "sinegen":
             return {"sinegen(scan+stream)": lambda: ops.sinegen(f0[..., 0], P, SR, w["dim"], self.rand_ini, seed=1)}
         if k == "srcmod":

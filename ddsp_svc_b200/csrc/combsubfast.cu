@@ -26,13 +26,17 @@
 #ifndef B2D_HOST_EMU               // tests/emu/ runs this kernel's source on the CPU (host_emu.h provides the shims)
 #include "b2d_common.cuh"
 #endif
-#include "fft1024.cuh"
+#include "fft_smem.cuh"
 
-using namespace b2d_fft1024;
+using namespace b2d_fft;
+using b2d_fft_smem::kThreads;
+using b2d_fft_smem::padi;
 
 namespace {
 
 constexpr int kP = 512;
+constexpr int kN = 1024;                                            // transform size: frames of 2 P
+constexpr int kPad = b2d_fft_smem::Plan<kN>::kPad, kTw2 = b2d_fft_smem::Plan<kN>::kTw2, kTw3 = b2d_fft_smem::Plan<kN>::kTw3;
 
 struct CfParams {
     const float* comb;         // [B, T]
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 4) combsubfast_kernel(CfParams p) {
 
     // ---- one-time tables ----
     for (int i = tid; i < kN; i += kThreads) win[i] = sqrtf(0.5f - 0.5f * cospif((float)i * (2.0f / kN)));
-    init_twiddles(tw2, tw3, tid);
+    b2d_fft_smem::init_twiddles<kN>(tw2, tw3, tid);
     __syncthreads();
 
     // windowed (comb + j noise) of frame q into `buf`; samples outside [0, T) are the zero padding (:766,772)

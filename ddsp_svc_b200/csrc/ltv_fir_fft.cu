@@ -14,7 +14,7 @@
 //     Y_g + j Y_{g+1} returns both.  Only signals of the SAME job are ever paired in one transform, so the fp32
 //     round-off of a loud channel (harmonic) never leaks into a quiet one (filtered noise);
 //   * all forward transforms of a pair (2 inputs + 1 impulse-response pair per job) run as one batch through the
-//     shared-memory Stockham passes of fft1024.cuh, then all inverse transforms as a second batch;
+//     shared-memory Stockham passes of fft_smem.cuh, then all inverse transforms as a second batch;
 //   * every 1021-sample output segment is overlap-added into a 4-hop ring per job at its delay-compensated position;
 //     a hop is complete once the segment of the FOLLOWING input hop has been added and is then written exactly once
 //     (y1, y2 and mix = y1 + y2 (+ addend)) with 128-bit stores -- deterministic, no atomics.

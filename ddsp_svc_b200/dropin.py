@@ -83,10 +83,17 @@ def patch_reference():
     from . import frontend                      # Volume_Extractor (numpy in -> numpy out like the reference, computed on the GPU)
     saved["Volume_Extractor"] = ref_vocoder.Volume_Extractor
     ref_vocoder.Volume_Extractor = frontend.Volume_Extractor
+    try:                                        # mel front end of the enhancer / diffusion vocoders (needs librosa to import)
+        import nsf_hifigan.nvSTFT as ref_stft
+        from . import mel
+        saved["STFT"] = ref_stft.STFT
+        ref_stft.STFT = mel.STFT
+    except ImportError as e:
+        saved.setdefault("_not_patched", {})["nsf_hifigan.nvSTFT"] = "%s: %s" % (type(e).__name__, e)
     try:
         import nsf_hifigan.models as ref_nsf
     except ImportError as e:                    # enhancer stack not importable: synthesizers only (reported below)
-        saved["_not_patched"] = {"nsf_hifigan.models": "%s: %s" % (type(e).__name__, e)}
+        saved.setdefault("_not_patched", {})["nsf_hifigan.models"] = "%s: %s" % (type(e).__name__, e)
         return saved
     saved["SineGen"] = ref_nsf.SineGen
     saved["SourceModuleHnNSF"] = ref_nsf.SourceModuleHnNSF
@@ -100,6 +107,9 @@ def unpatch_reference(saved):
     for name in ("Sins", "CombSub", "CombSubSuperFast", "CombSubFast", "Volume_Extractor"):
         if name in saved:
             setattr(ref_vocoder, name, saved[name])
+    if "STFT" in saved:
+        import nsf_hifigan.nvSTFT as ref_stft
+        ref_stft.STFT = saved["STFT"]
     if "SineGen" in saved:
         import nsf_hifigan.models as ref_nsf
         ref_nsf.SineGen = saved["SineGen"]

@@ -259,6 +259,15 @@ int b2d_mask_apply(float* signal, const float* mask_frames, int B, int n_mask_fr
  * k = linspace(0, 1, len_a - idx) evaluated in fp64.  Requires 0 <= idx < len_a and len_a - idx <= len_b. */
 int b2d_cross_fade(const float* a, int64_t len_a, const float* b, int64_t len_b, int64_t idx, float* out, void* stream);
 
+/* ---- log-mel front end of the NSF-HiFiGAN vocoder: STFT.get_mel, nsf_hifigan/nvSTFT.py:73-117 (keyshift 0, speed 1) ----
+ * audio [B, n_samples] -> mel [B, n_mels, n_frames], n_frames = b2d_mel_frames(...) (0 = signal too short):
+ * reflect / constant padding by (win - hop)/2, frames of win_size = n_fft = 2048 at `hop`, periodic Hann `window` [2048],
+ * magnitude sqrt(re^2 + im^2 + 1e-9), mel_basis [n_mels, n_fft/2 + 1] (librosa.filters.mel layout, n_mels <= 128),
+ * log(max(., clip_val)).  filter_lohi [n_mels, 2] (int32, device): first and one-past-last non-zero bin of each filter. */
+int b2d_mel_frames(int n_samples, int n_fft, int win_size, int hop);
+int b2d_mel_spectrogram(const float* audio, const float* window, const float* mel_basis, const int* filter_lohi, int B,
+                        int n_samples, int n_fft, int win_size, int hop, int n_mels, float clip_val, float* mel, void* stream);
+
 /* b2d_sins_synth: 0 (default) = 1 = separate oscillator-bank kernel next to the impulse-response builds, then the FIR
  * kernel; 2 = the bank is evaluated inside the FFT-domain FIR kernel (block 512, both filters <= 512 taps, <= 128
  * harmonics, FIR selection 0/4, else an error): one kernel computes bank, both FIRs and the mix and the [B, T] sinusoid

@@ -20,6 +20,8 @@ def test_algorithmic_bytes_match_the_survey():
     assert abs(per("sinegen") - 36.008) < 2e-3
     assert abs(per("srcmod") - 4.008) < 2e-3           # fused tanh(Linear(9 -> 1)): one value per sample
     assert abs(per("combsubfast") - 16.031) < 2e-3     # 3 x 513 control words per frame + 1 output
+    assert abs(per("mel") - 5.0) < 1e-6                # waveform in, 128 mels per 512-sample hop out
+    assert abs(per("maskmul") - 8.008) < 2e-3          # read + write in place, one mask value per frame
 
 
 def test_cpu_arm_runs_every_workload_kind():
@@ -29,13 +31,13 @@ def test_cpu_arm_runs_every_workload_kind():
     for name, w in bench.WORKLOADS.items():
         w = dict(w, B=1, sec=0.05)
         nF = max(2, syn.n_frames_for(w["sec"], bench.SR, bench.P))
-        sm = bench.split_map_of(w)
-        f0 = syn.make_f0(1, nF, bench.SR, bench.P)
-        ctrls = syn.make_ctrl(1, nF, sm)[1] if sm else None
+        if w["kind"] == "mel":
+            nF = 8                                       # one 2048-sample frame needs more than 0.05 s
+        f0, ctrls = bench.oracle_inputs(w, 1, nF)
         with torch.no_grad():
             out = bench.oracle_forward(w, f0, ctrls)
         key = "signal" if "signal" in out else "out"
-        assert out[key].shape[1] == nF * bench.P, name
+        assert out[key].shape[2 if w["kind"] == "mel" else 1] == (nF if w["kind"] == "mel" else nF * bench.P), name
 
 
 def test_reference_arm_prints_the_contract_line():
