@@ -21,12 +21,9 @@ from . import ops
 
 
 def _reference_unit2ctrl(n_unit, n_spk, split_map, **kw):
-    try:
-        from ddsp.unit2control import Unit2Control  # the reference's own class (not part of this repo)
-    except Exception as e:  # pragma: no cover - depends on the environment
-        raise RuntimeError(
-            "No unit2ctrl module was given and the reference's ddsp.unit2control.Unit2Control is not "
-            "importable; pass unit2ctrl=<module returning (controls dict, hidden)>.") from e
+    """The control network: this package's own Unit2Control (same parameter tree as the reference's
+    ddsp/unit2control.py, so its checkpoints load strictly; fused B200 kernels + library GEMMs, inference only)."""
+    from .unit2control import Unit2Control
     return Unit2Control(n_unit, n_spk, split_map, **kw)
 
 

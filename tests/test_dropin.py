@@ -34,10 +34,14 @@ def test_buffers_and_forward_signature_without_reference():
     assert "voiced_threshod" in inspect.signature(pkg.SourceModuleHnNSF.__init__).parameters   # reference spelling
     with pytest.raises(ValueError, match="Unknown Model"):
         dropin.build_model(dropin.DotDict({"model": {"type": "Nope"}, "data": {}}))
-    with pytest.raises(RuntimeError, match="unit2ctrl"):
-        if "ddsp.unit2control" in sys.modules:      # reference already imported by another test
-            raise RuntimeError("unit2ctrl")
-        pkg.Sins(44100, 512, 128, 256, 256)
+    # no unit2ctrl argument: the package's own Unit2Control (no dependency on the reference package), same head as the
+    # reference's (dense_out -> 640 outputs for Sins 128/256/256)
+    own = pkg.Sins(44100, 512, 128, 256, 256, n_unit=768)
+    from ddsp_svc_b200.unit2control import Unit2Control
+    assert isinstance(own.unit2ctrl, Unit2Control) and own.unit2ctrl.dense_out.weight_v.shape == (640, 256)
+    assert {"unit2ctrl.dense_out.weight_g", "unit2ctrl.dense_out.weight_v", "unit2ctrl.dense_out.bias"} <= set(own.state_dict())
+    with pytest.raises(ValueError, match="block_size"):
+        pkg.Sins(44100, 441, 128, 256, 256, unit2ctrl=pkg.FixedControls())          # unsupported shapes fail at build time
 
 
 def test_module_refuses_cpu_tensors():
