@@ -58,6 +58,7 @@ SIGNATURES = {
     "b2d_set_sinegen_impl": (ctypes.c_int, [ctypes.c_int]),
     "b2d_set_fft_arith": (ctypes.c_int, [ctypes.c_int]),
     "b2d_set_overlap": (ctypes.c_int, [ctypes.c_int]),
+    "b2d_split_tf32": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_size_t, c_stream]),
     "b2d_u2c_embed": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_int, c_f32p, ctypes.c_int,
                                      ctypes.c_int, c_stream]),
     "b2d_u2c_groupnorm_lrelu": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p,

@@ -162,7 +162,45 @@ __global__ void __launch_bounds__(256) u2c_softmax_feat_kernel(float* __restrict
         r[j] = is_query ? ratio * (expf(r[j] - diag - mx) + eps) : ratio * expf(r[j] - diag + eps);
 }
 
+// ---- fp32 -> (tf32 hi, tf32 lo) split for 3xTF32 library GEMMs: x = hi + lo + O(2^-22 |x|), both parts exactly
+// representable in TF32 (10-bit mantissa, round to nearest even on the dropped 13 bits) ----
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u = __float_as_uint(x);
+    u += 0x00000FFFu + ((u >> 13) & 1u);
+    return __uint_as_float(u & 0xFFFFE000u);
+}
+__global__ void __launch_bounds__(256) u2c_split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
+                                                             size_t n4, const float* __restrict__ xt, float* __restrict__ hit,
+                                                             float* __restrict__ lot, int tail) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 h, l;
+        h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+        l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+        hi[i] = h; lo[i] = l;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) {
+        const float v = xt[threadIdx.x], h = tf32_rn(v);
+        hit[threadIdx.x] = h; lot[threadIdx.x] = tf32_rn(v - h);
+    }
+}
+
 }  // namespace
+
+extern "C" int b2d_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
+    if (!x || !hi || !lo) return b2d::fail(B2D_ERR_NULL, "split_tf32: null pointer");
+    if (n == 0) return 0;
+    if (!b2d::aligned16(x) || !b2d::aligned16(hi) || !b2d::aligned16(lo)) return b2d::fail(B2D_ERR_ALIGN, "split_tf32: buffers must be 16-byte aligned");
+    const size_t n4 = n / 4;
+    const int tail = (int)(n - n4 * 4);
+    size_t gx = (n4 + 255) / 256;
+    if (gx > 148 * 16) gx = 148 * 16;
+    if (gx == 0) gx = 1;
+    u2c_split_tf32_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                                                          reinterpret_cast<float4*>(lo), n4, x + n4 * 4, hi + n4 * 4,
+                                                                          lo + n4 * 4, tail);
+    return b2d::check_launch("split_tf32");
+}
 
 extern "C" int b2d_u2c_embed(float* x, const float* f0, const float* phase, const float* volume, const float* embed_table,
                              const float* spk, int spk_rows, const float* aug_shift, int B, int T, void* stream) {

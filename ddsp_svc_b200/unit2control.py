@@ -119,7 +119,67 @@ def _k(lib_call, what):
     _count(1)
 
 
+def _split(x):
+    """x -> (hi, lo): TF32-exact parts with hi + lo = x to 2^-22 (csrc/unit2control.cu, b2d_split_tf32)."""
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _k(_lib.lib().b2d_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "b2d_split_tf32")
+    return hi, lo
+
+
+class _Gemm:
+    """The library GEMMs of the control network at one of three precisions.
+
+    * ``"3xtf32"`` (default): every product runs as THREE tensor-core GEMMs on TF32-exact operand halves, a_hi b_hi +
+      a_lo b_hi + a_hi b_lo with fp32 accumulation -- fp32-grade results (measured 5e-7 relative on the controls, like the
+      SIMT fp32 GEMM) at tensor-core speed; the halves come from b2d_split_tf32 (weights: once per checkpoint).
+    * ``"fp32"``: cuBLAS SIMT fp32 GEMMs (what the reference's Linear layers run on a GPU).
+    * ``"tf32"``: one TF32 pass (1e-3 relative per product, 3e-4 on the controls; the reference's cuDNN convolutions do
+      this under torch's defaults and land at 1.4e-4).
+    The TF32 modes flip torch.backends.cuda.matmul.allow_tf32 around their own calls only."""
+
+    def __init__(self, mode):
+        if mode not in ("3xtf32", "fp32", "tf32"):
+            raise ValueError("gemm_precision must be '3xtf32', 'fp32' or 'tf32'")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.mode != "fp32"
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+    def linear(self, x2d, w, bias):
+        """x2d [N, K] @ w^T + bias; ``w`` is a packed weight: [O, K] tensor, or (hi, lo) pair in 3xtf32 mode."""
+        if self.mode != "3xtf32":
+            return torch.addmm(bias, x2d, w.t())
+        xh, xl = _split(x2d)
+        wh, wl = w
+        out = torch.addmm(bias, xh, wh.t())
+        out.addmm_(xl, wh.t())
+        out.addmm_(xh, wl.t())
+        return out
+
+    def matmul(self, a, b):
+        """batched a @ b of two activations (the per-head contractions of the linear attention: 256 small problems).
+        In 3xtf32 mode these stay fp32 SIMT: cuBLAS serves batched TF32 problems of this shape with sm_80 kernels that are
+        slower than its fp32 path here (measured), and splitting both activations costs two more passes."""
+        if self.mode != "3xtf32":
+            return torch.matmul(a, b)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            return torch.matmul(a, b)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+
 class Unit2Control(nn.Module):
+    #: precision of the library GEMMs, see _Gemm: "3xtf32" (default, fp32-grade on the tensor cores), "fp32", "tf32"
+    gemm_precision = "3xtf32"
+
     def __init__(self, input_channel, n_spk, output_splits, use_pitch_aug=False, pcmer_norm=False, use_naive_v2=False,
                  use_conv_stack=True):
         super().__init__()
@@ -145,7 +205,8 @@ class Unit2Control(nn.Module):
 
     # ---- weights in the layouts the GEMMs / kernels want, rebuilt when a parameter changes (load_state_dict, .to) ----
     def _pack(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((b.data_ptr(), b._version) for b in self.buffers())
+        key = (self.gemm_precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.buffers())
         c = self.__dict__.get("_packed")
         if c is not None and c[0] == key:
             return c[1]
@@ -170,7 +231,8 @@ class Unit2Control(nn.Module):
                 L["ln_w"], L["ln_b"] = layer.norm.weight.detach().contiguous(), layer.norm.bias.detach().contiguous()
                 L["qkv_w"] = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight]).detach().contiguous()
                 L["qkv_b"] = torch.cat([a.to_q.bias, a.to_k.bias, a.to_v.bias]).detach().contiguous()
-                L["proj_t"] = a.fast_attention.projection_matrix.detach().t().contiguous()              # [64, 266]
+                # feature projection with the d^-1/4 data normaliser folded in (pcmer.py:18,30): [64, 266]
+                L["proj_t"] = (a.fast_attention.projection_matrix.detach() * (a.dim_head ** -0.25)).t().contiguous()
                 L["out_w"], L["out_b"] = a.to_out.weight.detach(), a.to_out.bias.detach()
                 L["cln_w"], L["cln_b"] = net[0].weight.detach().contiguous(), net[0].bias.detach().contiguous()
             dw = layer.conformer.dw_conv()
@@ -180,18 +242,27 @@ class Unit2Control(nn.Module):
             layers.append(L)
         P["layers"] = layers
         P["n_w"], P["n_b"] = self.norm.weight.detach().contiguous(), self.norm.bias.detach().contiguous()
-        P["do_w"], P["do_b"] = self.dense_out.weight.detach().contiguous(), self.dense_out.bias.detach()   # g v / |v| (weight_norm)
+        # weight_norm (old style): w = g v / |v| per output row.  `.weight` itself is only refreshed by the module's forward
+        # pre-hook (which never runs here), so it is recomputed from weight_g / weight_v
+        P["do_w"] = torch._weight_norm(self.dense_out.weight_v.detach(), self.dense_out.weight_g.detach(), 0).contiguous()
+        P["do_b"] = self.dense_out.bias.detach()
+        if self.gemm_precision == "3xtf32":          # weights of every GEMM as TF32-exact (hi, lo) pairs, once per checkpoint
+            for d in [P] + layers:
+                for name in [n for n in d if n.endswith("_w") and n[:-2] in ("c1", "c2", "qkv", "out", "pw1", "pw2", "do")]:
+                    d[name] = _split(d[name].contiguous())
+                if "proj_t" in d:
+                    d["proj"] = _split(d["proj_t"].t().contiguous())        # [J, d] like a Linear weight
         self.__dict__["_packed"] = (key, P)
         return P
 
     # ---- building blocks ----
     @staticmethod
-    def _conv3(x, w, b):
+    def _conv3(g, x, w, b):
         """Conv1d(k = 3, padding 1) on token-major x [B, T, I] as ONE GEMM over the three shifted inputs."""
         xp = torch.nn.functional.pad(x, (0, 0, 1, 1))
         T = x.shape[1]
         cat = torch.cat((xp[:, 0:T], xp[:, 1:T + 1], xp[:, 2:T + 2]), dim=-1)
-        return torch.addmm(b, cat.reshape(-1, cat.shape[-1]), w.t()).reshape(x.shape[0], T, -1)
+        return g.linear(cat.reshape(-1, cat.shape[-1]), w, b).reshape(x.shape[0], T, -1)
 
     @staticmethod
     def _layernorm(x, w, b):
@@ -200,55 +271,60 @@ class Unit2Control(nn.Module):
                                         b.data_ptr(), 1e-5, _stream()), "b2d_u2c_layernorm")
         return y
 
-    def _conv_module(self, x, L, pre_norm):
+    def _conv_module(self, g_, x, L, pre_norm):
         B, T, C = x.shape
         h = self._layernorm(x, L["cln_w"], L["cln_b"]) if pre_norm else x
-        h = torch.addmm(L["pw1_b"], h.reshape(-1, C), L["pw1_w"].t())                       # [B T, 4 C]: value | gate
+        h = g_.linear(h.reshape(-1, C), L["pw1_w"], L["pw1_b"])                              # [B T, 4 C]: value | gate
         inner = L["dw_w"].shape[0]
         g = torch.empty(B, T, inner, dtype=torch.float32, device=x.device)
         _k(_lib.lib().b2d_u2c_glu_dwconv_silu(h.data_ptr(), L["dw_w"].data_ptr(), L["dw_b"].data_ptr(), g.data_ptr(), B, T, inner,
                                               L["dw_w"].shape[1], _stream()), "b2d_u2c_glu_dwconv_silu")
-        return torch.addmm(L["pw2_b"], g.reshape(-1, inner), L["pw2_w"].t()).reshape(B, T, C)
+        return g_.linear(g.reshape(-1, inner), L["pw2_w"], L["pw2_b"]).reshape(B, T, C)
 
-    def _attention(self, x, L):
+    def _attention(self, g_, x, L):
         """performer self-attention of one PCmer layer on LayerNorm(x) (pcmer.py:148, :220-229, :283-309, :343-381)"""
         B, T, C = x.shape
         a = self.decoder._layers[0].attn
         H, d = a.heads, a.dim_head
         h = self._layernorm(x, L["ln_w"], L["ln_b"])
-        qkv = torch.addmm(L["qkv_b"], h.reshape(-1, C), L["qkv_w"].t()).reshape(B, T, 3, H, d)
+        qkv = g_.linear(h.reshape(-1, C), L["qkv_w"], L["qkv_b"]).reshape(B, T, 3, H, d)
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).contiguous() for i in range(3))        # [B, H, T, d]
         if self.pcmer_norm:
             q = q / (q.norm(dim=-1, keepdim=True) + 1e-8)
             k = k / (k.norm(dim=-1, keepdim=True) + 1e-8)
         J = L["proj_t"].shape[1]
         feats = []
+        zero_bias = torch.zeros(J, device=x.device)
         for data, is_q in ((q, 1), (k, 0)):
-            dd = torch.mm((d ** -0.25) * data.reshape(-1, d), L["proj_t"])                 # [B H T, J]
+            dd = g_.linear(data.reshape(-1, d), L["proj"] if g_.mode == "3xtf32" else L["proj_t"].t(), zero_bias)   # [B H T, J]
             _k(_lib.lib().b2d_u2c_softmax_features(dd.data_ptr(), data.data_ptr(), dd.shape[0], J, d, is_q, 1e-4, _stream()),
                "b2d_u2c_softmax_features")
             feats.append(dd.reshape(B, H, T, J))
         qf, kf = feats
         k_sum = kf.sum(dim=-2)                                                               # [B, H, J]
         d_inv = 1.0 / (torch.einsum("bhnj,bhj->bhn", qf, k_sum) + 1e-8)
-        context = torch.matmul(kf.transpose(-1, -2), v)                                      # [B, H, J, d]
-        out = torch.matmul(qf, context) * d_inv.unsqueeze(-1)                                # [B, H, T, d]
+        context = g_.matmul(kf.transpose(-1, -2), v)                                         # [B, H, J, d]
+        out = g_.matmul(qf, context) * d_inv.unsqueeze(-1)                                   # [B, H, T, d]
         out = out.permute(0, 2, 1, 3).reshape(B * T, H * d)
-        return torch.addmm(L["out_b"], out, L["out_w"].t()).reshape(B, T, C)
+        return g_.linear(out, L["out_w"], L["out_b"]).reshape(B, T, C)
 
     @torch.no_grad()
     def forward(self, units, f0, phase, volume, spk_id=None, spk_mix_dict=None, aug_shift=None):
         """units B x n_frames x n_unit; f0, phase, volume B x n_frames x 1 -> (dict of B x n_frames x feat, hidden)"""
+        with _Gemm(self.gemm_precision) as g:
+            return self._forward(g, units, f0, phase, volume, spk_id, spk_mix_dict, aug_shift)
+
+    def _forward(self, g, units, f0, phase, volume, spk_id=None, spk_mix_dict=None, aug_shift=None):
         _need_cuda_f32("units", units)
         B, T, _ = units.shape
         P = self._pack()
         L = _lib.lib()
-        x = self._conv3(units, P["c1_w"], P["c1_b"])
+        x = self._conv3(g, units, P["c1_w"], P["c1_b"])
         if self.use_conv_stack:
             stats = torch.empty(B * 4 * 2, dtype=torch.float64, device=x.device)
             _k(L.b2d_u2c_groupnorm_lrelu(x.data_ptr(), B, T, 256, 4, P["gn_w"].data_ptr(), P["gn_b"].data_ptr(), 1e-5, 0.01,
                                          stats.data_ptr(), _stream()), "b2d_u2c_groupnorm_lrelu")
-            x = self._conv3(x, P["c2_w"], P["c2_b"])
+            x = self._conv3(g, x, P["c2_w"], P["c2_b"])
         spk, spk_rows = None, 1
         if self.n_spk is not None and self.n_spk > 1:
             if spk_mix_dict is not None:
@@ -268,8 +344,8 @@ class Unit2Control(nn.Module):
            "b2d_u2c_embed")
         for Ly in P["layers"]:
             if not self.use_naive_v2:
-                x = x + self._attention(x, Ly)
-            x = x + self._conv_module(x, Ly, pre_norm=not self.use_naive_v2)
+                x = x + self._attention(g, x, Ly)
+            x = x + self._conv_module(g, x, Ly, pre_norm=not self.use_naive_v2)
         x = self._layernorm(x, P["n_w"], P["n_b"])
-        e = torch.addmm(P["do_b"], x.reshape(-1, 256), P["do_w"].t()).reshape(B, T, self.n_out)
+        e = g.linear(x.reshape(-1, 256), P["do_w"], P["do_b"]).reshape(B, T, self.n_out)
         return split_to_dict(e, self.output_splits), x

@@ -1,8 +1,9 @@
 """Acceptance run on the GPU: the reference's OWN call (main.py:259, `model(seg_units, seg_f0, seg_volume, spk_id=...,
 spk_mix_dict=...)` under torch.no_grad, then `seg_output *= mask` in place, main.py:260) executed twice on the same
 device -- once with the unmodified reference classes under eager PyTorch, once after `patch_reference()` through the
-reference's own `load_model` -- with the reference's real Unit2Control (real torch.split views of dense_out, real
-spk_id embedding / spk_mix_dict), and the waveforms compared.
+reference's own `load_model` (which then builds this package's synthesizers AND its Unit2Control, loaded strictly from
+the reference's checkpoint) -- real torch.split views of dense_out, real spk_id embedding / spk_mix_dict -- and the
+waveforms compared.
 
 Needs the reference sources: the live checkout in the build container or the staged copy baseline/_ref/
 (tools/stage_reference.py, travels to the GPU box); skipped when neither exists.
@@ -85,6 +86,10 @@ def test_main_py_call_reference_vs_patched(kind, tmp_path):
     torch.save({"global_step": 1, "model": ref_model.state_dict()}, tmp_path / "model_1.pt")
 
     refs = []
+    # the reference's control network runs cuDNN convolutions, which use TF32 by default (1e-3 relative): compare against its
+    # true fp32 result
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
         for kw in calls:
             drawn = []
@@ -95,6 +100,7 @@ def test_main_py_call_reference_vs_patched(kind, tmp_path):
             assert (drawn[0][0] == "rand") == case["uniform"]
             refs.append((seg_output.clone(), hidden.clone(), s_h.clone(), s_n.clone(), noise.reshape(1, -1).clone()))
 
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     saved = pkg.patch_reference()
     try:
         with contextlib.redirect_stdout(io.StringIO()):
@@ -104,8 +110,8 @@ def test_main_py_call_reference_vs_patched(kind, tmp_path):
             for kw, (r_sig, r_hid, r_h, r_n, noise) in zip(calls, refs):
                 # (1) same noise samples -> the whole signal is comparable
                 sig, hidden, (s_h, s_n) = model(units, f0, volume, noise=noise, **kw)
-                # same Unit2Control on the same device; its phase input comes from the phase-scan kernel (1 ulp)
-                assert torch.allclose(hidden, r_hid, atol=1e-4, rtol=1e-4)
+                # this package's Unit2Control (fused kernels + fp32 library GEMMs) against the reference's class in fp32
+                assert util.rms((hidden - r_hid).cpu()) < 1e-4 * max(util.rms(r_hid.cpu()), 1e-6)
                 tol = case.get("tol", GATE_RMS)
                 e = util.rms((sig - r_sig).cpu())
                 report.record("acceptance/%s/%s" % (kind, "mix" if kw["spk_mix_dict"] else "spk"), err=e,
