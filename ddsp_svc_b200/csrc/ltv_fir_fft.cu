@@ -40,7 +40,7 @@ constexpr int kRing = 4 * kHop;          // power of two: slot = (t - t_lo) & (k
 
 struct FftFirJob {
     const float* x;    // [B, T] or nullptr -> in-kernel uniform noise
-    const float* ir;   // [B, nF, L]
+    const float* ir;   // [B, nF, L] impulse responses; SPEC variant: [B, nF, N/2] float2 packed spectra (ir_spectrum_kernel)
     float* y;          // [B, T] or nullptr
     int L;
 };
@@ -73,8 +73,10 @@ struct FftFirParams {
 };
 
 constexpr int kBankRow = 128;            // harmonics per activated amplitude row of the BANK variant (H <= 128)
-template <int N, int NJ, int NBANK = 0> constexpr size_t fir_fft_smem() {
-    return (size_t)3 * NJ * Plan<N>::kPad * sizeof(float2) + (size_t)(Plan<N>::kTw2 + Plan<N>::kTw3) * sizeof(float2) +
+// SPEC variant: the spectra of the impulse responses are read from memory (ir_spectrum_kernel made them once per frame),
+// so the HH buffers and a quarter of the transforms disappear: 2 NJ buffers -> 53.4 KB for N = 1024, NJ = 2 -> 4 CTAs per SM
+template <int N, int NJ, int NBANK = 0, bool SPEC = false> constexpr size_t fir_fft_smem() {
+    return (size_t)(SPEC ? 2 : 3) * NJ * Plan<N>::kPad * sizeof(float2) + (size_t)(Plan<N>::kTw2 + Plan<N>::kTw3) * sizeof(float2) +
            (size_t)NJ * kRing * sizeof(float) + (NBANK ? (size_t)5 * kBankRow * sizeof(float) : 0);
 }   // N = 1024: NJ = 2 -> 70528 B (3 CTAs per SM), NJ = 1 -> 36224 B;  N = 2048: NJ = 1 -> 64384 B, NJ = 2 -> 124800 B
 
@@ -86,15 +88,16 @@ __device__ __forceinline__ void split2(float2 zk, float2 zm, float2& A, float2& 
 
 // PK: complex additions as packed f32x2 instructions (fft_regs.cuh Ar<true>): same results, fewer issue slots
 // NBANK: 0 = inputs from memory / Philox; 4 or 8 = job 0 is the sinusoid bank with that many bases of 16 harmonics
-template <int N, int NJ, bool PK, int NBANK = 0>
-__global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_fir_fft_kernel(FftFirParams p) {
+// SPEC: job[j].ir holds the packed 1024-point spectra of the impulse responses instead of the taps
+template <int N, int NJ, bool PK, int NBANK = 0, bool SPEC = false>
+__global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : (SPEC ? 4 : 3)) ltv_fir_fft_kernel(FftFirParams p) {
     constexpr int kN = N, kPad = Plan<N>::kPad, kTw2 = Plan<N>::kTw2, kTw3 = Plan<N>::kTw3;
     constexpr int kBins = N / 2 / kThreads;          // bins k = tid + 128 u per thread (DC.. N/2-1); Nyquist on thread 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // buffer b of the batch lives at F + b * kPad:  XA(j) = j  (hop g; later the paired output of job j),
     // XB(j) = NJ + j (hop g+1),  HH(j) = 2 NJ + j (impulse responses of frames g+1 and g+2)
     float2* F = reinterpret_cast<float2*>(smem_raw);
-    float2* tw2 = F + 3 * NJ * kPad;
+    float2* tw2 = F + (SPEC ? 2 : 3) * NJ * kPad;
     float2* tw3 = tw2 + kTw2;
     float* ring = reinterpret_cast<float*>(tw3 + kTw3);          // [NJ][kRing]
     float* bank_act = ring + NJ * kRing;                         // BANK: [3][128] activated amplitudes of frames g, g+1, g+2
@@ -182,24 +185,44 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
     // bit-identical for any G, batch split or shard.  Hop -1 (the partner of hop 0) does not exist: zeros.
     const int gs = h0 - 1, ge = min(h1, nF - 1);
 
+    // SPEC: packed spectrum row of frame f (clamped) of job j: [0] = (DC, Nyquist), [k] = H[k] for k = 1 .. N/2-1
+    auto spec_row = [&](int j, int f) -> const float2* {
+        return reinterpret_cast<const float2*>(p.job[j].ir) + ((size_t)b * nF + min(max(f, 0), nF - 1)) * (kN / 2);
+    };
+
     // ---- prologue: spectra of frame gs ----
+    if (SPEC) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs - 1, gs, true);    // exactly the (h_{g+1}, h_{g+2}) pair of hops gs-2, gs-1
-    __syncthreads();
-    fft_forward<N, NJ, PK, true>(F + 2 * NJ * kPad, tw2, tw3, tid);
+        for (int j = 0; j < NJ; ++j) {
+            const float2* row = spec_row(j, gs);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const float2* H = F + (2 * NJ + j) * kPad;
-#pragma unroll
-        for (int u = 0; u < kBins; ++u) {
-            const int k = tid + u * kThreads;
-            float2 unused;
-            if (k == 0) Hp[j][u] = make_float2(H[padi(0)].y, 0.f);
-            else split2(H[padi(k)], H[padi(kN - k)], unused, Hp[j][u]);
+            for (int u = 0; u < kBins; ++u) {
+                const int k = tid + u * kThreads;
+                const float2 h = __ldg(row + k);
+                Hp[j][u] = k == 0 ? make_float2(h.x, 0.f) : h;
+                if (k == 0) HpN[j] = h.y;
+            }
         }
-        HpN[j] = H[padi(kN / 2)].y;                                 // only thread 0 uses it
+        __syncthreads();                                                // twiddles and the cleared rings
+    } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) load_ir_pair(j, gs - 1, gs, true);    // exactly the (h_{g+1}, h_{g+2}) pair of hops gs-2, gs-1
+        __syncthreads();
+        fft_forward<N, NJ, PK, true>(F + 2 * NJ * kPad, tw2, tw3, tid);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float2* H = F + (2 * NJ + j) * kPad;
+#pragma unroll
+            for (int u = 0; u < kBins; ++u) {
+                const int k = tid + u * kThreads;
+                float2 unused;
+                if (k == 0) Hp[j][u] = make_float2(H[padi(0)].y, 0.f);
+                else split2(H[padi(k)], H[padi(kN - k)], unused, Hp[j][u]);
+            }
+            HpN[j] = H[padi(kN / 2)].y;                                 // only thread 0 uses it
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // write hop h (complete) from the rings: y_j, mix; clear its ring slots
     auto emit = [&](int h) {
@@ -259,10 +282,10 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
                 load_x(j, g, has_a, F + j * kPad);
                 load_x(j, g + 1, has_b, F + (NJ + j) * kPad);
             }
-            load_ir_pair(j, g + 1, g + 2, true);
+            if (!SPEC) load_ir_pair(j, g + 1, g + 2, true);
         }
         __syncthreads();
-        fft_forward<N, 3 * NJ, PK, true>(F, tw2, tw3, tid);      // all six have zero upper halves: pruned first pass
+        fft_forward<N, (SPEC ? 2 : 3) * NJ, PK, true>(F, tw2, tw3, tid);   // all have zero upper halves: pruned first pass
 
         // ---- Y_g = X_g H_g + XU_g (H_{g+1} - H_g),  Y_{g+1} = X_{g+1} H_{g+1} + XU_{g+1} (H_{g+2} - H_{g+1});
         //      paired as Y_g + j Y_{g+1} (Hermitian extension), stored re/im-swapped over XA(j) ----
@@ -270,7 +293,14 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
         for (int j = 0; j < NJ; ++j) {
             float2* XA = F + j * kPad;
             const float2* XB = F + (NJ + j) * kPad;
-            const float2* HH = F + (2 * NJ + j) * kPad;
+            const float2* HH = F + (2 * NJ + j) * kPad;                 // (!SPEC)
+            const float2* rowA = SPEC ? spec_row(j, g + 1) : nullptr;     // (SPEC) spectra of frames g+1, g+2
+            const float2* rowB = SPEC ? spec_row(j, g + 2) : nullptr;
+            float2 HaR[kBins], HbR[kBins];
+            if (SPEC) {
+#pragma unroll
+                for (int u = 0; u < kBins; ++u) { HaR[u] = __ldg(rowA + tid + u * kThreads); HbR[u] = __ldg(rowB + tid + u * kThreads); }
+            }
 #pragma unroll
             for (int u = 0; u < kBins; ++u) {
                 const int k = tid + u * kThreads;
@@ -279,7 +309,8 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
                 float2 Xa, XUa, Xb, XUb, Ha, Hb;
                 split2(XA[ik], XA[im], Xa, XUa);
                 split2(XB[ik], XB[im], Xb, XUb);
-                split2(HH[ik], HH[im], Ha, Hb);
+                if (SPEC) { Ha = HaR[u]; Hb = HbR[u]; }
+                else split2(HH[ik], HH[im], Ha, Hb);
                 const float2 ya = Ar<PK>::add(cmul(Xa, Hp[j][u]), cmul(XUa, Ar<PK>::sub(Ha, Hp[j][u])));
                 const float2 yb = Ar<PK>::add(cmul(Xb, Ha), cmul(XUb, Ar<PK>::sub(Hb, Ha)));
                 // Y[k] = ya + j yb;  Y[N-k] = conj(ya) + j conj(yb);  stored as (im, re)
@@ -288,8 +319,11 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
                 Hp[j][u] = Hb;
             }
             if (tid == 0) {      // DC and Nyquist: every spectrum involved is real there
-                const float2 a0 = XA[padi(0)], b0 = XB[padi(0)], z0 = HH[padi(0)];           // (X, XU), (X, XU), (H_{g+1}, H_{g+2})
-                const float2 aN = XA[padi(kN / 2)], bN = XB[padi(kN / 2)], zN = HH[padi(kN / 2)];
+                const float2 a0 = XA[padi(0)], b0 = XB[padi(0)];                              // (X, XU), (X, XU)
+                const float2 aN = XA[padi(kN / 2)], bN = XB[padi(kN / 2)];
+                // (H_{g+1}, H_{g+2}) at DC and at Nyquist
+                const float2 z0 = SPEC ? make_float2(HaR[0].x, HbR[0].x) : HH[padi(0)];
+                const float2 zN = SPEC ? make_float2(HaR[0].y, HbR[0].y) : HH[padi(kN / 2)];
                 const float hp0 = Hp[j][0].x, hpN = HpN[j];
                 const float ya0 = fmaf(a0.y, z0.x - hp0, a0.x * hp0), yb0 = fmaf(b0.y, z0.y - z0.x, b0.x * z0.x);
                 const float yaN = fmaf(aN.y, zN.x - hpN, aN.x * hpN), ybN = fmaf(bN.y, zN.y - zN.x, bN.x * zN.x);
@@ -334,6 +368,65 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : 3) ltv_
     if (ge < h1) emit(ge);                        // last hop of the utterance: no following input hop
 }
 
+// ---- impulse responses -> packed N-point spectra, once per frame (the SPEC variant of the FIR kernel reads them) ----
+// grid (frame groups of 8, utterance, job); frames 2m and 2m+1 of an utterance share one complex transform (pairs never
+// cross utterances and do not depend on the batch split: bit-identical output for any sharding); zero upper half -> pruned
+// first pass.  Row layout: N/2 float2 per frame, [0] = (H[0], H[N/2]) (both real), [k] = H[k].
+struct IrSpecParams {
+    const float* ir[2];
+    float2* spec[2];
+    int L[2];
+    int nF;
+};
+
+template <int N, bool PK>
+__global__ void __launch_bounds__(kThreads) ir_spectrum_kernel(IrSpecParams p) {
+    constexpr int kN = N, kPad = Plan<N>::kPad, kTw2 = Plan<N>::kTw2, kTw3 = Plan<N>::kTw3, kQ = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* F = reinterpret_cast<float2*>(smem_raw);
+    float2* tw2 = F + kQ * kPad;
+    float2* tw3 = tw2 + kTw2;
+    const int tid = threadIdx.x, b = blockIdx.y, j = blockIdx.z, nF = p.nF, L = p.L[j];
+    const int f0 = blockIdx.x * 2 * kQ;
+    const float* ir = p.ir[j] + (size_t)b * nF * L;
+    float2* spec = p.spec[j] + (size_t)b * nF * (kN / 2);
+    init_twiddles<N>(tw2, tw3, tid);
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+        const int fa = f0 + 2 * q, fb = fa + 1;
+        const float* ra = ir + (size_t)min(fa, nF - 1) * L;
+        const float* rb = ir + (size_t)min(fb, nF - 1) * L;
+        float2* buf = F + q * kPad;
+#pragma unroll
+        for (int u = 0; u < kN / 2 / kThreads; ++u) {
+            const int tau = tid + u * kThreads;
+            const bool in = tau < L;
+            buf[padi(tau)] = make_float2((in && fa < nF) ? __ldg(ra + tau) : 0.f, (in && fb < nF) ? __ldg(rb + tau) : 0.f);
+        }
+    }
+    __syncthreads();
+    fft_forward<N, kQ, PK, true>(F, tw2, tw3, tid);
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+        const int fa = f0 + 2 * q, fb = fa + 1;
+        const float2* Z = F + q * kPad;
+#pragma unroll
+        for (int u = 0; u < kN / 2 / kThreads; ++u) {
+            const int k = tid + u * kThreads;
+            float2 A, C;
+            if (k == 0) {
+                const float2 z0 = Z[padi(0)], zN = Z[padi(kN / 2)];
+                A = make_float2(z0.x, zN.x);
+                C = make_float2(z0.y, zN.y);
+            } else {
+                split2(Z[padi(k)], Z[padi(kN - k)], A, C);
+            }
+            if (fa < nF) spec[(size_t)fa * (kN / 2) + k] = A;
+            if (fb < nF) spec[(size_t)fb * (kN / 2) + k] = C;
+        }
+    }
+}
+
 }  // namespace
 
 #ifndef B2D_HOST_EMU
@@ -345,16 +438,16 @@ bool ltv_fir_fft_supported(int P, int taps1, int taps2, int njobs) {
     return P == kHop && taps1 > 0 && (njobs == 1 || taps2 > 0) && tmax <= 1024;
 }
 
-template <int N, int NJ, bool PK, int NBANK = 0>
+template <int N, int NJ, bool PK, int NBANK = 0, bool SPEC = false>
 static int launch_fir_fft_as(const FftFirParams& p, dim3 grid, cudaStream_t st) {
-    constexpr size_t smem = fir_fft_smem<N, NJ, NBANK>();
+    constexpr size_t smem = fir_fft_smem<N, NJ, NBANK, SPEC>();
     // per launch, like the direct-form kernels: function attributes are per device and this costs ~1 us
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK, NBANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK, NBANK, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "ltv_fir(fft): smem attr: %s", cudaGetErrorString(e));
     }
-    cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK, NBANK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    ltv_fir_fft_kernel<N, NJ, PK, NBANK><<<grid, kThreads, smem, st>>>(p);
+    cudaFuncSetAttribute(ltv_fir_fft_kernel<N, NJ, PK, NBANK, SPEC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    ltv_fir_fft_kernel<N, NJ, PK, NBANK, SPEC><<<grid, kThreads, smem, st>>>(p);
     return check_launch("ltv_fir(fft)");
 }
 
@@ -417,6 +510,46 @@ int sins_fused_launch(const float* f0, const double* frame_phase, const float* c
     const bool pk = g_fft_packed.load(std::memory_order_relaxed) != 0;
     if (H <= 64) return pk ? launch_fir_fft_as<1024, 2, true, 4>(p, grid, st) : launch_fir_fft_as<1024, 2, false, 4>(p, grid, st);
     return pk ? launch_fir_fft_as<1024, 2, true, 8>(p, grid, st) : launch_fir_fft_as<1024, 2, false, 8>(p, grid, st);
+}
+
+// ---- spectrum path (Sins): ir_spectrum_kernel once per call, then the SPEC variant of the FIR kernel ----
+bool fir_spec_supported(int P, int taps1, int taps2) {
+    return P == kHop && taps1 > 0 && taps2 > 0 && taps1 <= kHop && taps2 <= kHop && !(taps1 & 1) && !(taps2 & 1);
+}
+size_t fir_spec_floats(int B, int nF) { return (size_t)B * nF * 1024; }        // N/2 float2 per frame
+
+int ir_spectrum_launch(const float* ir1, int taps1, float* spec1, const float* ir2, int taps2, float* spec2, int B, int nF,
+                       cudaStream_t st) {
+    if (!fir_spec_supported(kHop, taps1, taps2)) return fail(B2D_ERR_UNSUPPORTED, "ir_spectrum: needs <= %d taps", kHop);
+    if (!aligned16(spec1) || !aligned16(spec2)) return fail(B2D_ERR_ALIGN, "ir_spectrum: spectra must be 16-byte aligned");
+    if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "ir_spectrum: batch %d > 65535", B);
+    IrSpecParams p;
+    p.ir[0] = ir1; p.ir[1] = ir2; p.L[0] = taps1; p.L[1] = taps2; p.nF = nF;
+    p.spec[0] = reinterpret_cast<float2*>(spec1); p.spec[1] = reinterpret_cast<float2*>(spec2);
+    constexpr size_t smem = (size_t)4 * Plan<1024>::kPad * sizeof(float2) + (size_t)(Plan<1024>::kTw2 + Plan<1024>::kTw3) * sizeof(float2);
+    const dim3 grid((unsigned)((nF + 7) / 8), B, 2);
+    if (g_fft_packed.load(std::memory_order_relaxed)) ir_spectrum_kernel<1024, true><<<grid, kThreads, smem, st>>>(p);
+    else ir_spectrum_kernel<1024, false><<<grid, kThreads, smem, st>>>(p);
+    return check_launch("ir_spectrum");
+}
+
+int ltv_fir_fft_spec_launch(const float* x1, const float* spec1, int taps1, float* y1, const float* x2, const float* spec2,
+                            int taps2, float* y2, float* mix, uint64_t seed, int64_t utt_off, int B, int nF, int P, cudaStream_t st) {
+    if (!fir_spec_supported(P, taps1, taps2)) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir(spec): needs block %d and <= %d taps", kHop, kHop);
+    const float* ptrs[] = {x1, x2, y1, y2, mix};
+    for (const float* q : ptrs)
+        if (q && !aligned16(q)) return fail(B2D_ERR_ALIGN, "ltv_fir(spec): signal pointers must be 16-byte aligned");
+    if (B > 65535) return fail(B2D_ERR_UNSUPPORTED, "ltv_fir(spec): batch %d > 65535", B);
+    FftFirParams p = {};
+    p.job[0] = {x1, spec1, y1, taps1};
+    p.job[1] = {x2, spec2, y2, taps2};
+    p.addend = nullptr; p.mix = mix; p.seed = seed; p.utt_off = utt_off; p.nF = nF;
+    int G = 32;
+    while (G > 2 && (long long)B * ((nF + G - 1) / G) < 148LL * 2) G >>= 1;
+    p.G = G;
+    const dim3 grid((unsigned)((nF + p.G - 1) / p.G), B);
+    return g_fft_packed.load(std::memory_order_relaxed) ? launch_fir_fft_as<1024, 2, true, 0, true>(p, grid, st)
+                                                        : launch_fir_fft_as<1024, 2, false, 0, true>(p, grid, st);
 }
 
 }  // namespace b2d

@@ -49,7 +49,7 @@ inline void launch(unsigned gx, unsigned gy, unsigned threads, const std::functi
             pool.reserve(threads);
             for (unsigned t = 0; t < threads; ++t)
                 pool.emplace_back([=, &kernel] {
-                    t_idx.x = t; b_idx.x = bx; b_idx.y = by;
+                    t_idx.x = t; b_idx.x = bx; b_idx.y = by; b_idx.z = 0;   // the emulated grid is 2-D
                     kernel();
                 });
             for (auto& th : pool) th.join();

@@ -180,3 +180,72 @@ def test_random_shapes_fuzz(emu):
         if add is not None:
             want = want + add
         assert np.array_equal(out["mix"], want), tag
+
+
+# ---- spectrum path: ir_spectrum_kernel + the SPEC variant of the FIR kernel (impulse-response spectra read from memory) ----
+@pytest.fixture(scope="module")
+def emu_spec(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libemu_firfft_spec.so")
+    cmd = ["g++", "-std=c++20", "-O2", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", so,
+           os.path.join(HERE, "emu", "emu_ltv_fir_fft.cpp")]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    lib = ctypes.CDLL(so)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.emu_ltv_fir_fft_spec.argtypes = [fp, fp, ctypes.c_int, fp, fp, fp, ctypes.c_int, fp, fp, ctypes.c_ulonglong,
+                                         ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp]
+    lib.emu_ltv_fir_fft_spec.restype = ctypes.c_int
+
+    def run(x1, ir1, x2, ir2, hops=32, seed=0, utt_off=0):
+        B, nF, L1 = ir1.shape
+        T = nF * P
+        keep = []
+
+        def ptr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            keep.append(a)
+            return ctypes.cast(a.ctypes.data, fp)
+
+        outs = {k: np.full((B, T), np.nan, np.float32) for k in ("y1", "y2", "mix")}
+        spec = [np.full((B, nF, 1024), np.nan, np.float32) for _ in range(2)]
+        optr = lambda a: ctypes.cast(a.ctypes.data, fp)
+        rc = lib.emu_ltv_fir_fft_spec(ptr(x1), ptr(ir1), L1, optr(outs["y1"]), ptr(x2), ptr(ir2), ir2.shape[2], optr(outs["y2"]),
+                                      optr(outs["mix"]), seed, utt_off, B, nF, hops, optr(spec[0]), optr(spec[1]))
+        assert rc == 0
+        outs["spec1"], outs["spec2"] = spec
+        return outs
+
+    return run
+
+
+@pytest.mark.parametrize("nF,hops,L1,L2", [(1, 32, 510, 510), (2, 2, 510, 510), (7, 4, 510, 254), (9, 2, 128, 512), (33, 32, 510, 510),
+                                           (12, 8, 2, 510)])
+def test_spectrum_path_matches_closed_form_and_packed_spectra(emu_spec, nF, hops, L1, L2):
+    x1, ir1 = _case(2, nF, L1, 11)
+    x2, ir2 = _case(2, nF, L2, 12)
+    out = emu_spec(x1, ir1, x2, ir2, hops=hops)
+    # the packed rows are the 1024-point spectra of the zero-padded taps: [0] = (DC, Nyquist), [k] = H[k]
+    for ir, spec in ((ir1, out["spec1"]), (ir2, out["spec2"])):
+        H = np.fft.rfft(ir.astype(np.float64), 1024, axis=-1)
+        got = spec.reshape(*ir.shape[:2], 512, 2)
+        assert np.abs(got[..., 0, 0] - H[..., 0].real).max() < 2e-6 and np.abs(got[..., 0, 1] - H[..., 512].real).max() < 2e-6
+        assert np.abs((got[..., 1:, 0] + 1j * got[..., 1:, 1]) - H[..., 1:512]).max() < 2e-6
+    t1 = cf.ltv_fir(x1.astype(np.float64), ir1.astype(np.float64), P)
+    t2 = cf.ltv_fir(x2.astype(np.float64), ir2.astype(np.float64), P)
+    assert not np.isnan(out["y1"]).any() and not np.isnan(out["mix"]).any()
+    assert np.abs(out["y1"] - t1).max() < 5e-6 and np.abs(out["y2"] - t2).max() < 5e-6
+    assert np.array_equal(out["mix"], out["y1"] + out["y2"])
+
+
+def test_spectrum_path_is_bit_identical_for_any_chunking_and_shard(emu_spec):
+    nF = 13
+    x1, ir1 = _case(3, nF, 510, 21)
+    _, ir2 = _case(3, nF, 510, 22)
+    a = emu_spec(x1, ir1, None, ir2, hops=32, seed=5)
+    b = emu_spec(x1, ir1, None, ir2, hops=2, seed=5)
+    for k in ("y1", "y2", "mix"):
+        assert np.array_equal(a[k], b[k]), k
+    part = emu_spec(x1[1:], ir1[1:], None, ir2[1:], hops=4, seed=5, utt_off=1)
+    assert np.array_equal(a["y2"][1:], part["y2"]) and np.array_equal(a["mix"][1:], part["mix"])
