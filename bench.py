@@ -592,7 +592,7 @@ def main():
                     help="A/B switch for the time-varying FIR kernel (ops.set_fir_impl)")
     ap.add_argument("--fft-arith", default="packed", choices=["scalar", "packed"],
                     help="A/B switch: packed f32x2 complex additions in the FFT kernels (ops.set_fft_arith)")
-    ap.add_argument("--sins-impl", default="auto", choices=["auto", "split", "fused"],
+    ap.add_argument("--sins-impl", default="auto", choices=["auto", "split", "fused", "spectrum"],
                     help="A/B switch (ops.set_sins_impl): bank fused into the FFT-domain FIR kernel, or separate kernels")
     ap.add_argument("--overlap", type=int, default=None,
                     help="A/B switch (ops.set_overlap): 0 in order, 1 impulse responses beside the bank, k >= 2 "

@@ -231,9 +231,11 @@ def sins_synth(f0_frames, frame_phase, c_amp, c_group_delay, c_noise, block, sam
                           int(block), H, Ma, Mn, float(sampling_rate), 0 if infer else 1, signal.data_ptr(),
                           _ptr(harmonic), _ptr(noise), ws.data_ptr(), ws_bytes, _stream())
     _lib.check(rc, "b2d_sins_synth")
-    fused = _sins_impl == "fused" and Ma == Mn and int(block) == 512 and Ma <= 257 and H <= 128 and _fir_impl in ("auto", "fft")
+    fft_ok = int(block) == 512 and max(Ma, Mn) <= 257 and _fir_impl in ("auto", "fft")
+    fused = _sins_impl == "fused" and Ma == Mn and fft_ok and H <= 128
+    spectrum = _sins_impl == "spectrum" and fft_ok
     nsplit = max(1, min(abs(_overlap_mode), B)) if abs(_overlap_mode) >= 2 else 1
-    _count(3 if fused else 2 + nsplit * (2 if Ma == Mn else 3))
+    _count(3 if fused else 5 if spectrum else 2 + nsplit * (2 if Ma == Mn else 3))
     return signal, harmonic, noise
 
 
@@ -430,7 +432,8 @@ def set_overlap(mode):
 
 
 def set_sins_impl(name):
-    """'auto' (= 'split': separate bank kernel, measured faster) | 'split' | 'fused' (bank inside the FFT-domain FIR kernel)."""
+    """'auto' (= 'split': separate bank kernel, measured fastest) | 'split' | 'fused' (bank inside the FFT-domain FIR kernel)
+    | 'spectrum' (impulse-response spectra from their own kernel, read by the FIR kernel)."""
     global _sins_impl
-    _lib.check(_lib.lib().b2d_set_sins_impl({"auto": 0, "split": 1, "fused": 2}[name]), "b2d_set_sins_impl")
+    _lib.check(_lib.lib().b2d_set_sins_impl({"auto": 0, "split": 1, "fused": 2, "spectrum": 3}[name]), "b2d_set_sins_impl")
     _sins_impl = name

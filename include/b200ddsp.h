@@ -296,11 +296,14 @@ int b2d_mel_frames(int n_samples, int n_fft, int win_size, int hop);
 int b2d_mel_spectrogram(const float* audio, const float* window, const float* mel_basis, const int* filter_lohi, int B,
                         int n_samples, int n_fft, int win_size, int hop, int n_mels, float clip_val, float* mel, void* stream);
 
-/* b2d_sins_synth: 0 (default) = 1 = separate oscillator-bank kernel next to the impulse-response builds, then the FIR
- * kernel; 2 = the bank is evaluated inside the FFT-domain FIR kernel (block 512, both filters <= 512 taps, <= 128
- * harmonics, FIR selection 0/4, else an error): one kernel computes bank, both FIRs and the mix and the [B, T] sinusoid
- * tensor is never materialised -- measured 1.4 % slower on B200 (see api.cu), kept as a tested alternative.  Same results
- * (identical bank arithmetic).  Process-wide test/diagnostic knob (atomic, read once per call). */
+/* b2d_sins_synth variants.  0 (default) = 1 = oscillator-bank kernel next to the impulse-response builds, then the FIR
+ * kernel transforms the impulse responses itself.  2 = the bank is evaluated inside the FFT-domain FIR kernel (additionally <= 128 harmonics):
+ * no [B, T] sinusoid tensor, one launch less -- measured 1.4 % slower on B200 (see api.cu), kept as a tested alternative.
+ * 3 = spectrum path: a small kernel turns the impulse responses into packed 1024-point spectra once per frame (beside the
+ * bank), the FIR kernel reads them: a quarter fewer transforms, 53 instead of 70 KB of shared memory (4 CTAs per SM); needs
+ * block 512, both filters <= 512 taps, FIR selection 0/4; measured 4 % slower (the transform is only moved) -- the consumer
+ * side of a future impulse-response GEMM that emits spectra.  Set it BEFORE querying b2d_sins_workspace_bytes (the spectra
+ * live in the workspace).  All variants agree to round-off.  Process-wide test/diagnostic knob (atomic, read once per call). */
 int b2d_set_sins_impl(int impl);
 
 /* How b2d_sins_synth overlaps its independent kernels on an internal side stream that is joined on the caller's stream

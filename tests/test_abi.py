@@ -44,7 +44,13 @@ def test_argument_errors_do_not_touch_the_device(lib):
     assert lib.b2d_ltv_fir(16, 16, 511, 16, 0, 0, 0, 0, 0, 0, 0, 1, 1, 512, 0) == -2         # odd tap count
     assert lib.b2d_set_fir_impl(5) == -4
     assert lib.b2d_ltv_fir(4, 16, 510, 16, 0, 0, 0, 0, 0, 0, 0, 1, 1, 512, 0) == -3         # misaligned x
+    # sinusoids + two impulse-response tensors (+ two packed-spectrum tensors when the spectrum variant is selected)
     assert lib.b2d_sins_workspace_bytes(32, 861, 512, 256, 256) == 32 * 861 * 512 * 4 + 2 * 32 * 861 * 510 * 4
+    assert lib.b2d_set_sins_impl(3) == 0
+    assert lib.b2d_sins_workspace_bytes(32, 861, 512, 256, 256) == 32 * 861 * 512 * 4 + 2 * 32 * 861 * 510 * 4 + 2 * 32 * 861 * 1024 * 4
+    up = lambda v: (v + 255) // 256 * 256
+    assert lib.b2d_sins_workspace_bytes(2, 10, 256, 256, 256) == up(2 * 10 * 256 * 4) + 2 * up(2 * 10 * 510 * 4)   # block 256: no spectra
+    assert lib.b2d_set_sins_impl(0) == 0
     assert lib.b2d_dft_tables_bytes(256) == 2 * 256 * 128 * 4 + 16 * 8 * 128 * 8 * 4   # CUDA-core tables + tensor-core image
     assert lib.b2d_sins_synth(16, 16, 16, 16, 16, 640, 0, 0, 0, 16, 16, 1, 1, 512, 128, 256, 256, 44100.0, 0,
                               16, 16, 16, 256, 10, 0) == -5                                  # workspace too small

@@ -211,8 +211,8 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("H", [128, 64, 31, 1])
 def test_fused_bank_fir_kernel_equals_split_kernels(H):
-    """`fused` evaluates the oscillator bank inside the FFT-domain FIR kernel; `split` (the default) runs the stand-alone
-    bank kernel + FIR kernel.  Same bank arithmetic, same transforms: the three outputs must agree to round-off (the two
+    """`fused` evaluates the oscillator bank inside the FFT-domain FIR kernel; `split` runs the stand-alone bank kernel +
+    FIR kernel (the default); `spectrum` moves the impulse-response transforms into their own kernel.  Same bank arithmetic, same transforms: the three outputs must agree to round-off (the two
     compilations may contract differently), for full and partial harmonic groups, in-kernel and explicit noise."""
     B, nF = 3, 70
     sm = syn.sins_split_map(H, 256, 256)
@@ -223,7 +223,7 @@ def test_fused_bank_fir_kernel_equals_split_kernels(H):
     fp, _ = ops.phase_scan(f0, P, SR)
     outs = {}
     try:
-        for impl in ("split", "fused"):
+        for impl in ("split", "fused", "spectrum"):
             ops.set_sins_impl(impl)
             outs[impl] = [ops.sins_synth(f0, fp, dc["amplitudes"], dc["group_delay"], dc["noise_magnitude"], P, SR,
                                          noise_in=noise),
@@ -237,3 +237,10 @@ def test_fused_bank_fir_kernel_equals_split_kernels(H):
             worst = max(worst, (x - y).abs().max().item())
     report.record("sins_fused_vs_split/H%d" % H, max_diff=worst, identical=worst == 0.0)
     assert worst < 1e-7
+    # the spectrum path pairs the impulse responses differently in their transforms: round-off level differences
+    worst_s = 0.0
+    for a, b in zip(outs["split"], outs["spectrum"]):
+        for x, y in zip(a, b):
+            worst_s = max(worst_s, (x - y).abs().max().item())
+    report.record("sins_spectrum_vs_split/H%d" % H, max_diff=worst_s)
+    assert worst_s < 2e-7
