@@ -501,7 +501,9 @@ def time_other_workload(name, dev, flush, torch, steps=10, warmup=3):
         flush.zero_()
         a.record(); run.step(); b.record()
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    # median of the per-step times: these auxiliary lines share one process with the headline run, and a step that has to
+    # grow the caching allocator (SineGen's 1 GB output) would otherwise dominate a 10-step mean
+    ms = statistics.median(a.elapsed_time(b) for a, b in ev)
     e2e_ms = time_e2e(run, (4, 8, 12, 6, 2) if w["B"] >= 16 else 1, flush, 3, torch)
     kt = time_kernels(run, flush, 5, torch)
     peak, _ = measured_peak_hbm()
@@ -580,6 +582,8 @@ def main():
                     help="N>1, chunked peer modes: compute streams the chunks alternate between")
     ap.add_argument("--no-others", action="store_true",
                     help="skip the eager-PyTorch-on-GPU baseline and the `other_workloads` timings of the default run")
+    ap.add_argument("--e2e-only", action="store_true",
+                    help="host-buffer pipeline timing only (sweeps of --e2e-chunks / --e2e-streams): prints {e2e_ms}")
     ap.add_argument("--quick", action="store_true",
                     help="device-timed step only: skip the host-buffer e2e, per-kernel and CPU legs (sweeps)")
     ap.add_argument("--e2e-chunks", default="4,8,12,6,2",
@@ -701,6 +705,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.e2e_only:
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                step()
+            ms = time_e2e(run, e2e_chunks, flush, max(5, min(args.steps, 20)), torch)
+        print(json.dumps({"e2e_only": True, "e2e_ms": ms, "chunks": args.e2e_chunks, "streams": args.e2e_streams,
+                          "value": B * T / (ms * 1e-3) / 1e6}))
+        return
     with torch.no_grad():
         for _ in range(args.warmup):
             step()

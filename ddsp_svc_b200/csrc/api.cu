@@ -365,30 +365,49 @@ extern "C" int b2d_combsub_synth(const float* f0_frames, const double* frame_pha
     float* ir_n = reinterpret_cast<float*>(ws + 3 * sBT + b2d::align_up(BF * La * 4, 256) + b2d::align_up(BF * Lh * 4, 256));
     cudaStream_t st = (cudaStream_t)stream;
 
+    // the dynamic-window impulse response (the largest of the three builds) is only needed by the LAST filter: it runs on
+    // the internal side stream beside the all-pass / noise stage and is joined right before the harmonic filter
+    b2d::SideLane* lane = b2d::g_overlap.load(std::memory_order_relaxed) != 0 ? b2d::side_lane() : nullptr;
+    cudaError_t je = cudaSuccess;
+    if (lane) {
+        je = cudaEventRecord(lane->fork, st);
+        if (je == cudaSuccess) je = cudaStreamWaitEvent(lane->hi, lane->fork, 0);
+        if (je != cudaSuccess) return b2d::fail((int)je, "combsub_synth: fork: %s", cudaGetErrorString(je));
+    }
+    const int rch = b2d_ir_build(c_harmonic, ctrl_stride, B2D_IR_MAG_DYNAMIC, f0_frames, dft_tables_harmonic, B, n_frames,
+                                 n_mag_harmonic, sampling_rate, ir_h, lane ? (void*)lane->hi : stream);
+    if (lane) je = cudaEventRecord(lane->join, lane->hi);
+    // from here on every return path must first join the side stream
+    auto joined = [&](int code) -> int {
+        if (lane && je == cudaSuccess) je = cudaStreamWaitEvent(st, lane->join, 0);
+        if (code) return code;
+        if (rch) return rch;
+        if (je != cudaSuccess) return b2d::fail((int)je, "combsub_synth: join: %s", cudaGetErrorString(je));
+        return 0;
+    };
     int rc = b2d_comb_source(f0_frames, frame_phase, B, n_frames, block, sampling_rate, round_fp32, comb, stream);
-    if (rc) return rc;
+    if (rc) return joined(rc);
     rc = b2d_ir_build(c_group_delay, ctrl_stride, B2D_IR_ALLPASS, nullptr, dft_tables_allpass, B, n_frames,
                       n_mag_allpass, sampling_rate, ir_ap, stream);
-    if (rc) return rc;
-    rc = b2d_ir_build(c_harmonic, ctrl_stride, B2D_IR_MAG_DYNAMIC, f0_frames, dft_tables_harmonic, B, n_frames,
-                      n_mag_harmonic, sampling_rate, ir_h, stream);
-    if (rc) return rc;
+    if (rc) return joined(rc);
     rc = b2d_ir_build(c_noise, ctrl_stride, B2D_IR_MAG_HANN, nullptr, dft_tables_noise, B, n_frames, n_mag_noise,
                       sampling_rate, ir_n, stream);
-    if (rc) return rc;
+    if (rc) return joined(rc);
     // all-pass on the comb and the noise filter: one launch when the tap counts agree
     if (La == Ln) {
         rc = b2d::ltv_fir_launch(comb, ir_ap, La, allp, noise_in, ir_n, Ln, nbuf, nullptr, nullptr, seed,
                                  utterance_offset, B, n_frames, block, st);
-        if (rc) return rc;
+        if (rc) return joined(rc);
     } else {
         rc = b2d::ltv_fir_launch(comb, ir_ap, La, allp, nullptr, nullptr, 0, nullptr, nullptr, nullptr, seed,
                                  utterance_offset, B, n_frames, block, st);
-        if (rc) return rc;
+        if (rc) return joined(rc);
         rc = b2d::ltv_fir_launch(noise_in, ir_n, Ln, nbuf, nullptr, nullptr, 0, nullptr, nullptr, nullptr, seed,
                                  utterance_offset, B, n_frames, block, st);
-        if (rc) return rc;
+        if (rc) return joined(rc);
     }
+    rc = joined(0);
+    if (rc) return rc;
     // harmonic magnitude filter on the all-passed comb; signal = harmonic + noise
     return b2d::ltv_fir_launch(allp, ir_h, Lh, harmonic, nullptr, nullptr, 0, nullptr, nbuf, signal, seed,
                                utterance_offset, B, n_frames, block, st);

@@ -128,13 +128,49 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : (SPEC ?
             buf[padi(tau)] = make_float2(in ? __ldg(ra + tau) : 0.f, (in && with_b) ? __ldg(rb + tau) : 0.f);
         }
     };
-    // x_j[gP + i] (1 + j i/P) for i < P, zeros above; `present` false -> all zeros (hop outside the chunk's reach)
-    auto load_x = [&](int j, int g, bool present, float2* buf) {
+    // Global loads of a hop pair (input samples read from memory, impulse-response taps), issued ONE ITERATION AHEAD into
+    // registers: they are in flight during the previous pair's transforms instead of stalling the head of the iteration
+    // (ncu, round 2: 18 % of the stall samples were long-scoreboard waits on exactly these loads).
+    constexpr int kTau = kN / 2 / kThreads;
+    struct Prefetch { float4 xa[NJ], xb[NJ]; float ha[NJ][kTau], hb[NJ][kTau]; };
+    auto fetch = [&](int g, Prefetch& q) {
+        const bool a_ok = g >= 0, b_ok = g + 1 <= nF - 1;
+        const int i0 = tid << 2;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            q.xa[j] = q.xb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.job[j].x && !(NBANK && j == 0)) {
+                const float* xr = p.job[j].x + (size_t)b * T + i0;
+                if (a_ok) q.xa[j] = __ldg(reinterpret_cast<const float4*>(xr + (size_t)g * kHop));
+                if (b_ok) q.xb[j] = __ldg(reinterpret_cast<const float4*>(xr + (size_t)(g + 1) * kHop));
+            }
+            if (!SPEC) {
+                const int L = p.job[j].L;
+                const float* base = p.job[j].ir + (size_t)b * nF * L;
+                const float* ra = base + (size_t)min(max(g + 1, 0), nF - 1) * L;
+                const float* rb = base + (size_t)min(max(g + 2, 0), nF - 1) * L;
+#pragma unroll
+                for (int u = 0; u < kTau; ++u) {
+                    const int tau = tid + u * kThreads;
+                    q.ha[j][u] = tau < L ? __ldg(ra + tau) : 0.f;
+                    q.hb[j][u] = tau < L ? __ldg(rb + tau) : 0.f;
+                }
+            }
+        }
+    };
+    auto put_ir_pair = [&](int j, const Prefetch& q) {
+        float2* buf = F + (2 * NJ + j) * kPad;
+#pragma unroll
+        for (int u = 0; u < kTau; ++u) buf[padi(tid + u * kThreads)] = make_float2(q.ha[j][u], q.hb[j][u]);
+    };
+    // x_j[gP + i] (1 + j i/P) for i < P, zeros above; `present` false -> all zeros (hop outside the chunk's reach);
+    // `pre` = the hop's samples when the job reads its input from memory (prefetched), else Philox noise is drawn here
+    auto load_x = [&](int j, int g, bool present, float4 pre, float2* buf) {
         const int i0 = tid << 2;
         const int m0 = g * kHop + i0;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (present) {
-            if (p.job[j].x) v = __ldg(reinterpret_cast<const float4*>(p.job[j].x + (size_t)b * T + m0));
+            if (p.job[j].x) v = pre;
             else v = b2d::philox_uniform_pm1(p.seed, utt, (uint32_t)(m0 >> 2));
         }
         const float s = 1.0f / kHop;
@@ -247,6 +283,8 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : (SPEC ?
         }
     };
 
+    Prefetch pf;
+    fetch(gs, pf);
 #pragma unroll 1
     for (int g = gs; g <= ge; g += 2) {
         const bool has_a = g >= 0, has_b = g + 1 <= nF - 1;      // properties of the utterance only, not of the chunking
@@ -279,12 +317,13 @@ __global__ void __launch_bounds__(kThreads, (N == 2048 && NJ == 2) ? 1 : (SPEC ?
             } else
 #endif
             {
-                load_x(j, g, has_a, F + j * kPad);
-                load_x(j, g + 1, has_b, F + (NJ + j) * kPad);
+                load_x(j, g, has_a, pf.xa[j], F + j * kPad);
+                load_x(j, g + 1, has_b, pf.xb[j], F + (NJ + j) * kPad);
             }
-            if (!SPEC) load_ir_pair(j, g + 1, g + 2, true);
+            if (!SPEC) put_ir_pair(j, pf);
         }
         __syncthreads();
+        if (g + 2 <= ge) fetch(g + 2, pf);                 // next pair's loads fly during this pair's transforms
         fft_forward<N, (SPEC ? 2 : 3) * NJ, PK, true>(F, tw2, tw3, tid);   // all have zero upper halves: pruned first pass
 
         // ---- Y_g = X_g H_g + XU_g (H_{g+1} - H_g),  Y_{g+1} = X_{g+1} H_{g+1} + XU_{g+1} (H_{g+2} - H_{g+1});

@@ -306,9 +306,10 @@ int b2d_mel_spectrogram(const float* audio, const float* window, const float* me
  * live in the workspace).  All variants agree to round-off.  Process-wide test/diagnostic knob (atomic, read once per call). */
 int b2d_set_sins_impl(int impl);
 
-/* How b2d_sins_synth overlaps its independent kernels on an internal side stream that is joined on the caller's stream
- * before the call returns (event record/wait only; legal under stream capture).  0: every kernel on the caller's
- * stream, in order.  1: impulse-response builds next to the oscillator bank.  k >= 2: additionally the batch is cut into
+/* How b2d_sins_synth / b2d_combsub_synth overlap their independent kernels on an internal side stream that is joined on
+ * the caller's stream before the call returns (event record/wait only; legal under stream capture).  0: every kernel on
+ * the caller's stream, in order.  1: Sins: impulse-response builds next to the oscillator bank; CombSub: the dynamic-window
+ * impulse response (needed by the last filter only) next to the comb source / all-pass / noise stage.  k >= 2: additionally the batch is cut into
  * k sub-batches that alternate between the two streams, staggered, so the FIR of one shares the SMs with the bank of the
  * next (-k: the same with a high-priority side stream).  Same results in every mode (the noise is keyed by the global
  * utterance index, the FFT-domain FIR is bit-identical for any batch split).  Process-wide test/diagnostic knob (atomic,

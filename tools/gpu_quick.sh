@@ -6,6 +6,6 @@ timeout 300 python -m pytest tests/test_gpu_ir_tc.py tests/test_gpu_sins.py test
 q() { name=$1; shift; timeout 120 python bench.py --quick --steps 20 --warmup 3 "$@" > gpurun_out/q_$name.json 2> gpurun_out/q_$name.err; echo "$name $(tail -1 gpurun_out/q_$name.json)"; }
 q sins
 q sins_split --sins-impl split
-q sins_spec_ov0 --overlap 0
+q sins_spectrum --sins-impl spectrum
 q cfg1 --workload sins_cfg1
 timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-others --breakdown > gpurun_out/b_quick.json 2> gpurun_out/b_quick.err; tail -2 gpurun_out/b_quick.err
