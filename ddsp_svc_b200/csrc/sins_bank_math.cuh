@@ -4,6 +4,12 @@
 #pragma once
 #include "b2d_common.cuh"
 
+// 1 (default since round 2: bank 0.307 -> 0.273 ms, parity unchanged): even anchors by double-angle chains (halves the SFU
+// work of the anchors); 0: every anchor by __sincosf (round-1 code)
+#ifndef B2D_BANK_DOUBLE_ANGLE
+#define B2D_BANK_DOUBLE_ANGLE 1
+#endif
+
 namespace b2d_bank {
 
 constexpr int kGroup = 128;  // harmonics per group = 16 anchors x 8 bases
@@ -53,8 +59,22 @@ __device__ __forceinline__ void bank_group(const float* __restrict__ arow, const
     const float4* d4 = reinterpret_cast<const float4*>(drow + group * kGroup);
     const float hbase = (float)(group * kGroup);
 
+#if B2D_BANK_DOUBLE_ANGLE
+    // Anchors in chains 1-2-4-8-16 | 3-6-12 | 5-10 | 7-14 | 9 | 11 | 13 | 15: only the odd anchors call the SFU (16 MUFU per
+    // sample instead of 32); an even anchor comes from its half by the double-angle identities sin 2x = 2 s c,
+    // cos 2x = 1 - 2 s^2 (3 FP32 operations).  The chain keeps ONE (sin, cos) pair per sample alive.  Error: each doubling
+    // doubles the absolute error of the pair; anchor 16 (four doublings from an argument in [-pi, pi], where the SFU is
+    // most accurate) carries ~16 x 2^-22, the same order as MUFU.SIN on the unreduced argument 16 phi it replaces.
+    constexpr int kOrder[kNA] = {0, 1, 3, 7, 15, 2, 5, 11, 4, 9, 6, 13, 8, 10, 12, 14};      // anchor index a - 1
+    constexpr bool kFresh[kNA] = {true, false, false, false, false, true, false, false, true, false, true, false, true, true, true, true};
+    float sa[4], ca[4];
+#pragma unroll
+    for (int i = 0; i < kNA; ++i) {
+        const int a = kOrder[i];
+#else
 #pragma unroll 2
     for (int a = 0; a < kNA; ++a) {
+#endif
         u64 Ap[4], Dp[4];
         {
             const float4 A0 = a4[2 * a], D0 = d4[2 * a];
@@ -69,9 +89,20 @@ __device__ __forceinline__ void bank_group(const float* __restrict__ arow, const
         const float af = (float)(a + 1);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
+#if B2D_BANK_DOUBLE_ANGLE
+            if (kFresh[i]) {
+                __sincosf(af * phase[s], &sa[s], &ca[s]);
+            } else {
+                const float so = sa[s], co = ca[s];
+                sa[s] = (2.0f * so) * co;
+                ca[s] = fmaf(-2.0f * so, so, 1.0f);
+            }
+            const u64 sc = pack2(sa[s], ca[s]), fr = pack2(frac[s], frac[s]);
+#else
             float sa, ca;
             __sincosf(af * phase[s], &sa, &ca);
             const u64 sc = pack2(sa, ca), fr = pack2(frac[s], frac[s]);
+#endif
 #pragma unroll
             for (int bp = 0; bp < NP; ++bp) {
                 float amp0, amp1;
