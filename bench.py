@@ -471,7 +471,7 @@ def time_e2e(run, chunks, flush, reps, torch):
         b.synchronize()
         if i > 0:
             ee.append(a.elapsed_time(b))
-    return sum(ee) / len(ee)
+    return statistics.median(ee)        # robust to a pass in which the host thread was descheduled while enqueueing
 
 
 def time_kernels(run, flush, reps, torch):
@@ -504,7 +504,7 @@ def time_other_workload(name, dev, flush, torch, steps=10, warmup=3):
     # median of the per-step times: these auxiliary lines share one process with the headline run, and a step that has to
     # grow the caching allocator (SineGen's 1 GB output) would otherwise dominate a 10-step mean
     ms = statistics.median(a.elapsed_time(b) for a, b in ev)
-    e2e_ms = time_e2e(run, (4, 8, 12, 6, 2) if w["B"] >= 16 else 1, flush, 3, torch)
+    e2e_ms = time_e2e(run, (6, 10, 10, 6) if w["B"] >= 16 else 1, flush, 5, torch)
     kt = time_kernels(run, flush, 5, torch)
     peak, _ = measured_peak_hbm()
     dom = max(kt, key=kt.get)
@@ -586,10 +586,10 @@ def main():
                     help="host-buffer pipeline timing only (sweeps of --e2e-chunks / --e2e-streams): prints {e2e_ms}")
     ap.add_argument("--quick", action="store_true",
                     help="device-timed step only: skip the host-buffer e2e, per-kernel and CPU legs (sweeps)")
-    ap.add_argument("--e2e-chunks", default="4,8,12,6,2",
+    ap.add_argument("--e2e-chunks", default="6,10,10,6",
                     help="utterance chunks of the host-buffer pipeline: a count (1 = serial) or comma-separated "
-                         "relative sizes (default tapered: short fill and drain; measured 2.57 ms vs 2.72 ms "
-                         "for 4 equal chunks on the Sins workload)")
+                         "relative sizes (default tapered: short fill and drain; round-2 sweep on the Sins workload, "
+                         "gpurun_out/e2e_sweep.txt: 6,10,10,6 -> 2.02 ms, 4,8,12,6,2 -> 2.10, 16,16 -> 2.35)")
     ap.add_argument("--e2e-streams", type=int, default=1,
                     help="compute streams of the host-buffer pipeline (HostPipeline(compute_streams=...); >1 not yet measured)")
     ap.add_argument("--fir-impl", default="auto", choices=["auto", "cuda", "tc", "cuda8", "fft"],
@@ -738,7 +738,7 @@ def main():
         # ---- end to end through the public module API with HOST buffers ----
         e2e_ms = float("nan")
         if not args.quick:
-            e2e_ms = time_e2e(run, e2e_chunks, flush, max(3, min(args.steps, 10)), torch)
+            e2e_ms = time_e2e(run, e2e_chunks, flush, max(10, min(args.steps, 20)), torch)
         clk = clocks.stop() if rank == 0 else None
 
         # ---- per-kernel durations (CUDA events on the launching stream), for the roofline ----
@@ -786,8 +786,9 @@ def main():
             "e2e": {"value": samples_step / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": run.h2d, "d2h_bytes_per_step": run.out_h.numel() * 4,
                     "what": "pinned host f0+controls -> H2D -> module forward -> D2H of the waveform, through "
-                            "ddsp_svc_b200.HostPipeline (utterance chunks %s; upload, kernels and download overlap)"
-                            % args.e2e_chunks},
+                            "ddsp_svc_b200.HostPipeline (utterance chunks %s; upload, kernels and download overlap); "
+                            "median of %d passes, each timed separately with the L2 flushed before it"
+                            % (args.e2e_chunks, max(10, min(args.steps, 20)))},
             "gpu_launches": launches,
             "clocks": clk,
         }
