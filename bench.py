@@ -245,12 +245,15 @@ def best_thread_count(w):
     best, best_t = ncpu, None
     for n in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
         torch.set_num_threads(n)
+        dt = None
         with torch.no_grad():
             oracle_forward(w, f0, ctrls)
-            t0 = time.perf_counter()
-            oracle_forward(w, f0, ctrls)
-            dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
+            for _ in range(2):                     # best of two: one noisy pass must not flip the choice between runs
+                t0 = time.perf_counter()
+                oracle_forward(w, f0, ctrls)
+                d = time.perf_counter() - t0
+                dt = d if dt is None else min(dt, d)
+        if best_t is None or dt < 0.95 * best_t:    # a larger pool must win by 5 % (ascending order: the smaller one stays on ties)
             best, best_t = n, dt
     _best_threads[key] = best
     return best
