@@ -604,7 +604,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=None,
                     help="A/B switch (ops.set_overlap): 0 in order, 1 impulse responses beside the bank, k >= 2 "
                          "additionally k staggered sub-batches on two streams")
-    ap.add_argument("--sinegen-impl", default="auto", choices=["auto", "v1", "v2", "v2p"],
+    ap.add_argument("--sinegen-impl", default="auto", choices=["auto", "v1", "v2", "v2p", "v2r7"],
                     help="A/B switch for the SineGen / source-module kernel (ops.set_sinegen_impl)")
     ap.add_argument("--breakdown", action="store_true", help="also print per-kernel times to stderr")
     args = ap.parse_args()

@@ -237,7 +237,8 @@ __device__ __forceinline__ float sin_turns(float theta) {
 // Measured dead ends (B200, 64 x 10 s x 9): compiling for 8 CTAs/SM (64 registers) 0.357 vs 0.345 ms -- the
 // kernel is bound by the issue slots / pipe mix, not by latency; a streaming variant (one Philox block -> 4
 // outputs -> one 128-bit shared store, 48 registers) 0.42 ms, 320 M vs 248 M warp instructions.
-template <int DIM, bool FUSED, int MODE>
+// ROUNDS: Philox rounds of the in-kernel noise (10 standard; 7 = `v2r7`, see b2d_common.cuh)
+template <int DIM, bool FUSED, int MODE, int ROUNDS = 10>
 __global__ void __launch_bounds__(kThreads4, 6) sinegen4_kernel(SgParams p) {
     extern __shared__ __align__(16) float tile[];  // [kTile4 * DIM]; untouched when FUSED without noise_in
     const int b = blockIdx.y;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kThreads4, 6) sinegen4_kernel(SgParams p) {
         } else {
 #pragma unroll
             for (int c = 0; c < DIM; ++c)
-                normals4(b2d::philox4x32_10(make_uint4(q0 + c, 0x51e6e004u, (uint32_t)utt, (uint32_t)(utt >> 32)), key), eps + 4 * c);
+                normals4(b2d::philox4x32<ROUNDS>(make_uint4(q0 + c, 0x51e6e004u, (uint32_t)utt, (uint32_t)(utt >> 32)), key), eps + 4 * c);
         }
         // per-sample frame quantities; consecutive samples share a frame except at a boundary
         int k, j;
@@ -371,12 +372,12 @@ __global__ void __launch_bounds__(kThreads4, 6) sinegen4_kernel(SgParams p) {
     }
 }
 
-template <int DIM, bool FUSED, int MODE>
+template <int DIM, bool FUSED, int MODE, int ROUNDS = 10>
 void launch_v2_as(const SgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     // 18 KB tiles x 6 resident CTAs: ask for the large shared-memory split (per launch: attributes are per device)
-    cudaFuncSetAttribute(sinegen4_kernel<DIM, FUSED, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(sinegen4_kernel<DIM, FUSED, MODE, ROUNDS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    sinegen4_kernel<DIM, FUSED, MODE><<<grid, kThreads4, smem, st>>>(p);
+    sinegen4_kernel<DIM, FUSED, MODE, ROUNDS><<<grid, kThreads4, smem, st>>>(p);
 }
 
 template <int DIM>
@@ -386,19 +387,21 @@ void launch_v2(const SgParams& p, int B, long long T, int impl, cudaStream_t st)
     const size_t smem = (!fused || p.noise_in) ? (size_t)kTile4 * DIM * sizeof(float) : 0;
     if (fused) {
         if (impl == 2) launch_v2_as<DIM, true, 0>(p, grid, smem, st);
+        else if (impl == 4) launch_v2_as<DIM, true, 0, 7>(p, grid, smem, st);
         else launch_v2_as<DIM, true, 1>(p, grid, smem, st);
     } else {
         if (impl == 2) launch_v2_as<DIM, false, 0>(p, grid, smem, st);
+        else if (impl == 4) launch_v2_as<DIM, false, 0, 7>(p, grid, smem, st);
         else launch_v2_as<DIM, false, 1>(p, grid, smem, st);
     }
 }
 
-std::atomic<int> g_sinegen_impl{0};   // 0 auto, 1 v1 (one sample per thread), 2 v2 scalar, 3 v2 packed f32x2
+std::atomic<int> g_sinegen_impl{0};   // 0 auto, 1 v1 (one sample per thread), 2 v2 scalar, 3 v2 packed f32x2, 4 v2 scalar with Philox-7 noise
 
 }  // namespace
 
 extern "C" int b2d_set_sinegen_impl(int impl) {
-    if (impl < 0 || impl > 3) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_sinegen_impl: %d not in 0..3", impl);
+    if (impl < 0 || impl > 4) return b2d::fail(B2D_ERR_UNSUPPORTED, "set_sinegen_impl: %d not in 0..4", impl);
     g_sinegen_impl.store(impl, std::memory_order_relaxed);
     return 0;
 }
@@ -457,7 +460,9 @@ static int sinegen_launch(const float* f0, const float* rand_ini, const float* n
     // mul.rn.f32x2 + add.rn.f32x2 pairs into FFMA2 (one rounding instead of the reference's two), which moves the sine
     // argument by an ulp: max error 3e-6 instead of 3e-8 against the reference (still inside the 2e-6 RMS gate)
     const int sel = g_sinegen_impl.load(std::memory_order_relaxed);
-    const int impl = sel == 0 ? 2 : sel;
+    // auto = four samples per thread, scalar arithmetic, Philox4x32-7 normals (round 2: 0.356 -> 0.318 ms, KS / correlation
+    // tests in tests/test_gpu_combsub_sinegen.py); 2 selects the same kernel with the standard 10 rounds
+    const int impl = sel == 0 ? 4 : sel;
     if (impl >= 2 && (dim == 9 || dim == 1)) {
         if (dim == 9) launch_v2<9>(p, B, T, impl, st);
         else launch_v2<1>(p, B, T, impl, st);

@@ -389,8 +389,9 @@ def source_module(f0, upp, sampling_rate, dim, rand_ini, linear_weight, linear_b
 
 
 def set_sinegen_impl(name):
-    """'auto' | 'v1' (one sample per thread) | 'v2' (four per thread) | 'v2p' (four per thread, packed f32x2)."""
-    impl = {"auto": 0, "v1": 1, "v2": 2, "v2p": 3}[name]
+    """'auto' | 'v1' (one sample per thread) | 'v2' (four per thread) | 'v2p' (four per thread, packed f32x2) | 'v2r7' (v2
+    with Philox4x32-7 instead of -10 for the in-kernel noise)."""
+    impl = {"auto": 0, "v1": 1, "v2": 2, "v2p": 3, "v2r7": 4}[name]
     _lib.check(_lib.lib().b2d_set_sinegen_impl(impl), "b2d_set_sinegen_impl")
 
 

@@ -316,11 +316,13 @@ int b2d_set_sins_impl(int impl);
  * read once per call). */
 int b2d_set_overlap(int mode);
 
-/* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto, 1 one sample per
- * thread (first kernel of round 1; also the only one for dim other than 1 or 9), 2 four samples per thread (auto),
+/* Kernel selection for b2d_sinegen / b2d_source_module (measurement and A/B tests): 0 auto (= 4), 1 one sample per
+ * thread (first kernel of round 1; also the only one for dim other than 1 or 9), 2 four samples per thread,
  * 3 four samples per thread with packed f32x2 arithmetic (3-5 % faster, but ptxas fuses its packed mul+add pairs, so
  * the sine argument is rounded once instead of twice: max error 3e-6 instead of 3e-8).  Impl 1 and 2/3 draw DIFFERENT in-kernel
- * noise streams (both Philox4x32-10 keyed by seed / global utterance / position). */
+ * noise streams (both Philox4x32-10 keyed by seed / global utterance / position).
+ * 4 = variant 2 with Philox4x32-7 instead of -10 for the in-kernel normals (7 rounds: the smallest count reported to
+ * pass BigCrush; 11 % faster; Kolmogorov-Smirnov / correlation tests in tests/test_gpu_combsub_sinegen.py). */
 int b2d_set_sinegen_impl(int impl);
 
 #ifdef __cplusplus

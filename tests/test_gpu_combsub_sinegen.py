@@ -235,7 +235,45 @@ def test_sinegen_kernel_variants_match_oracle(impl, upp, nF):
     assert (bm.double() - want).abs().max().item() < 2e-6
 
 
-@pytest.mark.parametrize("impl", ["v1", "v2p"])
+def test_sinegen_philox7_noise_statistics():
+    """`v2r7` draws its normals from Philox4x32-7 (the smallest round count reported to pass BigCrush) instead of -10.
+    Checked here on 2.4 M samples: Kolmogorov-Smirnov distance to N(0, 1), autocorrelation at lags 1..16 along time, correlation
+    between harmonics, between utterances, between different seeds and with the 10-round stream of the same counters."""
+    B, nF, upp, dim = 8, 64, 512, 9
+    f0 = torch.zeros(B, nF, device=DEV)
+    ri = torch.zeros(dim)
+    draw = lambda impl, seed: (ops.sinegen(f0, upp, SR, dim, ri, seed=seed) / (0.1 / 3)).double().cpu()
+    try:
+        ops.set_sinegen_impl("v2r7")
+        a, a2 = draw("v2r7", 21), draw("v2r7", 22)
+        assert torch.equal(a, draw("v2r7", 21))                         # deterministic per seed
+        ops.set_sinegen_impl("v2")
+        ten = draw("v2", 21)
+    finally:
+        ops.set_sinegen_impl("auto")
+    x = a.reshape(-1)
+    n = x.numel()
+    xs, _ = torch.sort(x)
+    cdf = 0.5 * (1 + torch.erf(xs / 2 ** 0.5))
+    i = torch.arange(1, n + 1, dtype=torch.float64)
+    ks = torch.max(torch.max(i / n - cdf), torch.max(cdf - (i - 1) / n)).item()
+    t = a[:, :, 0]                                                       # harmonic 0 along time, per utterance
+    t = t - t.mean(dim=1, keepdim=True)
+    lags = [float((t[:, :-k] * t[:, k:]).mean() / t.var()) for k in range(1, 17)]
+    flat = a.reshape(-1, dim)
+    cross_h = (torch.corrcoef(flat.T) - torch.eye(dim)).abs().max().item()
+    cross_u = abs(torch.corrcoef(torch.stack([a[0].reshape(-1), a[1].reshape(-1)]))[0, 1].item())
+    cross_seed = abs(torch.corrcoef(torch.stack([x, a2.reshape(-1)]))[0, 1].item())
+    cross_rounds = abs(torch.corrcoef(torch.stack([x, ten.reshape(-1)]))[0, 1].item())
+    report.record("sinegen_noise/v2r7_ks", n=n, ks=ks, ks_bound=1.63 / n ** 0.5, max_lag_corr=max(abs(v) for v in lags), cross_harmonic=cross_h,
+                  cross_utterance=cross_u, cross_seed=cross_seed, cross_rounds=cross_rounds, mean=x.mean().item(), var=x.var().item())
+    assert ks < 1.63 / n ** 0.5                                          # 1 % critical value of the KS test
+    tol = 4.5 / (n / dim) ** 0.5                                         # ~4.5 sigma of a sample correlation
+    assert max(abs(v) for v in lags) < 4.5 / (t.numel()) ** 0.5 * 1.5 and cross_h < tol * 1.5
+    assert cross_u < 4.5 / (n / B) ** 0.5 and cross_seed < 4.5 / n ** 0.5 and cross_rounds < 4.5 / n ** 0.5
+
+
+@pytest.mark.parametrize("impl", ["v1", "v2p", "v2r7"])
 def test_sinegen_in_kernel_noise_moments_per_variant(impl):
     B, nF, upp, dim = 4, 64, 512, 9
     f0 = torch.zeros(B, nF, device=DEV)            # unvoiced: out = (sine_amp/3) * eps, so eps is observable
