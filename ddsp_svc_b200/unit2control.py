@@ -179,6 +179,12 @@ class _Gemm:
 class Unit2Control(nn.Module):
     #: precision of the library GEMMs, see _Gemm: "3xtf32" (default, fp32-grade on the tensor cores), "fp32", "tf32"
     gemm_precision = "3xtf32"
+    #: PCmer: run the performer's linear attention (k-sum, context, normalised read-out) as ONE kernel per (utterance, head)
+    #: (csrc/linear_attention.cu) instead of two batched library GEMMs + eager elementwise passes.  Off by default: correct
+    #: (same 1.4e-6 on the controls) but measured SLOWER on B200 at B = 32 x 861 frames (12.6 vs 10.5 ms for the whole
+    #: network): 256 CTAs of 9 warps, two per SM, single-buffered tiles -- it needs a split over frames and double buffering
+    #: to beat the batched SIMT GEMMs.
+    fused_attention = False
 
     def __init__(self, input_channel, n_spk, output_splits, use_pitch_aug=False, pcmer_norm=False, use_naive_v2=False,
                  use_conv_stack=True):
@@ -301,6 +307,11 @@ class Unit2Control(nn.Module):
                "b2d_u2c_softmax_features")
             feats.append(dd.reshape(B, H, T, J))
         qf, kf = feats
+        if self.fused_attention and d == 64 and J <= 272:
+            out = torch.empty(B, T, H, d, dtype=torch.float32, device=x.device)
+            _k(_lib.lib().b2d_u2c_linear_attention(qf.data_ptr(), kf.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, T, J, d, 1e-8,
+                                                   _stream()), "b2d_u2c_linear_attention")
+            return g_.linear(out.reshape(B * T, H * d), L["out_w"], L["out_b"]).reshape(B, T, C)
         k_sum = kf.sum(dim=-2)                                                               # [B, H, J]
         d_inv = 1.0 / (torch.einsum("bhnj,bhj->bhn", qf, k_sum) + 1e-8)
         context = g_.matmul(kf.transpose(-1, -2), v)                                         # [B, H, J, d]

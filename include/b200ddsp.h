@@ -286,6 +286,11 @@ int b2d_u2c_glu_dwconv_silu(const float* in, const float* weight, const float* b
                             int inner_channels, int kernel_size, void* stream);
 int b2d_u2c_softmax_features(float* projected, const float* data, int rows, int n_features, int dim_head, int is_query,
                              float eps, void* stream);
+/* Fused non-causal linear attention of the performer layers (ddsp/pcmer.py:220-229), one CTA per (utterance, head):
+ * q_features, k_features [B*H, T, n_features] (the feature maps above), v [B*H, T, dim_head] ->
+ * out [B, T, H, dim_head] = (q' . (k'^T v)) / (q' . sum_t k' + eps).  dim_head must be 64, n_features <= 272. */
+int b2d_u2c_linear_attention(const float* q_features, const float* k_features, const float* v, float* out, int B, int H,
+                             int T, int n_features, int dim_head, float eps, void* stream);
 
 /* ---- log-mel front end of the NSF-HiFiGAN vocoder: STFT.get_mel, nsf_hifigan/nvSTFT.py:73-117 (keyshift 0, speed 1) ----
  * audio [B, n_samples] -> mel [B, n_mels, n_frames], n_frames = b2d_mel_frames(...) (0 = signal too short):

@@ -13,6 +13,8 @@
 #include "emu_combsubfast.cpp"
 #elif defined(TSAN_SUPERFAST)
 #include "emu_superfast.cpp"
+#elif defined(TSAN_LINATTN)
+#include "emu_linear_attention.cpp"
 #else
 #define B2D_HOST_EMU 1
 #include "host_emu.h"
@@ -52,6 +54,12 @@ int main(int argc, char** argv) {
     emu_combsubfast(comb.data(), dense.data(), dense.data() + 513, dense.data() + 1026, C, noise.data(), 1, 0, B, nF, 4, out.data());
     emu_combsubfast(comb.data(), dense.data(), dense.data() + 513, dense.data() + 1026, C, nullptr, 1, 0, B, nF, 32, out.data());
     for (float v : out) s += v;
+#elif defined(TSAN_LINATTN)
+    const int B = 1, H = 2, T = 37, J = 266;
+    std::vector<float> qf(B * H * T * J), kf(B * H * T * J), v(B * H * T * 64), out(B * T * H * 64);
+    fill(qf, 0.1f, 0.5f); fill(kf, 0.1f, 0.5f); fill(v, 1.f);
+    emu_linear_attention(qf.data(), kf.data(), v.data(), out.data(), B, H, T, J, 1e-8f);
+    for (float e : out) s += e;
 #elif defined(TSAN_SUPERFAST)
     const int B = 1, nF = 9, T = nF * 512, C = 4 * 1025;
     std::vector<float> par(B * nF * 4), noise(B * T), dense(B * nF * C), out(B * T);

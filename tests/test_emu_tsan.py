@@ -38,7 +38,7 @@ def test_detector_sees_a_missing_barrier_and_accepts_a_correct_one(tmp_path):
     assert "ThreadSanitizer" not in good.stderr and good.returncode == 0, good.stderr[-2000:]
 
 
-@pytest.mark.parametrize("define", ["TSAN_FIRFFT", "TSAN_CSFAST", "TSAN_SUPERFAST"])
+@pytest.mark.parametrize("define", ["TSAN_FIRFFT", "TSAN_CSFAST", "TSAN_SUPERFAST", "TSAN_LINATTN"])
 def test_kernel_source_has_no_shared_memory_race(tmp_path, define):
     exe = _build(tmp_path, define.lower(), define)
     res = _run(exe)

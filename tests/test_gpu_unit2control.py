@@ -18,6 +18,7 @@ DEV = "cuda:0"
 
 VARIANTS = {
     "pcmer_sins": (dict(), {"amplitudes": 128, "group_delay": 256, "noise_magnitude": 256}),
+    "pcmer_sins_fused_attention": (dict(), {"amplitudes": 128, "group_delay": 256, "noise_magnitude": 256}),
     "naive_superfast": (dict(use_naive_v2=True, use_conv_stack=True, use_pitch_aug=True),
                         {"harmonic_magnitude": 1025, "harmonic_phase": 1025, "noise_magnitude": 1025, "noise_phase": 1025}),
     "pcmer_norm_plainconv": (dict(pcmer_norm=True, use_conv_stack=False), {"a": 33, "b": 7}),
@@ -48,6 +49,7 @@ def test_unit2control_matches_the_reference_class(name):
     assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
     ours.load_state_dict(ref.state_dict())                # strict
     ours = ours.to(DEV).eval()
+    ours.fused_attention = name.endswith("fused_attention")      # the opt-in one-kernel linear attention (csrc/linear_attention.cu)
     B, T = 2, 150
     units, f0, phase, volume = _inputs(B, T, 768, 4)
     calls = [dict(spk_id=torch.LongTensor([[2], [3]])), dict(spk_id=torch.LongTensor([[1]]), spk_mix_dict={1: 0.25, 3: 0.75})]

@@ -27,6 +27,9 @@ if ref_loader.available():
         for mode in ("3xtf32", "fp32", "tf32"):
             m = copy.copy(ours); m.gemm_precision = mode; m.__dict__["_packed"] = None
             models.append(("b200_" + mode, m))
+        if not kw:
+            m = copy.copy(ours); m.fused_attention = False; m.__dict__["_packed"] = None
+            models.append(("b200_3xtf32_unfused_attention", m))
         for tag, m in models:
             with torch.no_grad():
                 got = torch.cat(list(m(u, f0, ph, vo)[0].values()), -1).cpu()
@@ -37,9 +40,5 @@ if ref_loader.available():
                 a.record()
                 for _ in range(5): m(u, f0, ph, vo)
                 b.record(); b.synchronize()
-            print("unit2control %-16s %-34s %7.3f ms   controls rel rms err vs reference CPU fp32 %.2e" % (name, tag, a.elapsed_time(b) / 5, err))
-        from torch.profiler import profile, ProfilerActivity
-        with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
-            models[1][1](u, f0, ph, vo); torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
+            print("unit2control %-16s %-40s %7.3f ms   controls rel rms err vs reference CPU fp32 %.2e" % (name, tag, a.elapsed_time(b) / 5, err))
 PY
