@@ -64,7 +64,9 @@ __device__ __forceinline__ float mask_weight(const float* __restrict__ m, int nF
     const float lam = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
     const int i1 = i0 + (i0 < nF_mask ? 1 : 0);
     const float v0 = m[min(i0, nF_mask - 1)], v1 = m[min(i1, nF_mask - 1)];
-    return (1.f - lam) * v0 + lam * v1;
+    // torch's CPU kernel evaluates w0 * v0 + w1 * v1 as fma(w0, v0, w1 * v1) (checked bit for bit on general frame values in
+    // tests/test_oracle_frontend.py); written out so the result does not depend on the compiler's contraction choice
+    return fmaf(1.f - lam, v0, __fmul_rn(lam, v1));
 }
 
 template <bool VEC>

@@ -43,3 +43,24 @@ def test_restatement_equals_the_live_reference_on_fresh_inputs():
         a, b = g.standard_normal(400).astype(np.float32), g.standard_normal(500).astype(np.float32)
         for idx in (0, 1, 250, 399):
             assert np.array_equal(fe.cross_fade(a, b, idx), cf(a, b, idx))
+
+
+def test_interpolation_weight_arithmetic_of_the_mask_kernel_equals_torch():
+    """csrc/frontend.cu::mask_weight restated in numpy (fp32 operation by operation: scale = f32(nF) / f32(nF P),
+    src = scale * f32(t), lambda = src - floor(src), w = fma(1 - lambda, v0, lambda * v1)) against torch's
+    upsample_linear1d(align_corners=True) on GENERAL frame values, power-of-two and other block sizes: bit-identical."""
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    for P in (512, 441, 300, 256, 7):
+        for nF in (1, 3, 46, 259):
+            m = rng.standard_normal(nF).astype(f32)
+            ref = fe.upsample(torch.from_numpy(m)[None, :, None], P)[0, :, 0].numpy()
+            t = np.arange(nF * P, dtype=np.int64)
+            src = (f32(nF) / f32(nF * P) * t.astype(f32)).astype(f32)
+            i0 = np.minimum(np.floor(src).astype(np.int64), nF)
+            lam = np.clip((src - i0.astype(f32)).astype(f32), 0, 1).astype(f32)
+            i1 = i0 + (i0 < nF)
+            v0, v1 = m[np.minimum(i0, nF - 1)], m[np.minimum(i1, nF - 1)]
+            w0 = (f32(1) - lam).astype(f32)
+            w = ((lam * v1).astype(f32).astype(np.float64) + w0.astype(np.float64) * v0.astype(np.float64)).astype(f32)   # fma
+            assert np.array_equal(w, ref), (P, nF)
